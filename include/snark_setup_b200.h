@@ -1,0 +1,155 @@
+/*
+ * snark_setup_b200.h — C ABI of the B200-native batch-exponentiation engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of nimiq/snark-setup: every
+ * entry point takes plain pointers and sizes, host memory unless the name ends in `_dev`, and
+ * replaces the body of the reference function cited beside it.  The reference has no FFI today;
+ * INTEGRATION.md shows the Rust `extern "C"` block + `build.rs` a maintainer adds so that
+ * `setup_utils::{batch_exp, batch_mul, generate_powers_of_tau, merge_pairs, power_pairs,
+ * check_subgroup}`, `phase1::helpers::buffers::apply_powers` and
+ * `phase1::helpers::accumulator::check_*` call into this library.
+ *
+ * Conventions
+ *   - Points cross the boundary in the reference's canonical serialisation (ark-serialize 0.4):
+ *     packed elements, no header; `compressed` selects x+flags vs x||y+flags
+ *     (sizes: BLS12-377 G1 48/96, G2 96/192; BW6-761 G1 = G2 = 96/192,
+ *     phase1/src/objects/parameters.rs:312-317).
+ *   - Scalars cross as canonical little-endian integers < r of ss_scalar_size() bytes
+ *     (32 for BLS12-377, 48 for BW6-761) = `Fr::serialize_uncompressed`.
+ *   - `check` is setup_utils::CheckForCorrectness (setup-utils/src/elements.rs:18-23).
+ *   - Return value: SS_OK or an ss_status error; details of the last error of the calling thread
+ *     via ss_last_error().  Errors map 1:1 onto setup_utils::Error (setup-utils/src/errors.rs:11-38).
+ *   - The caller owns every buffer; nothing is retained after return; only the bytes of the
+ *     output range are written.  Entry points are thread-safe (the reference calls the helpers from
+ *     up to 4 rayon tasks at once, phase1/src/computation.rs:68-188).
+ *   - There is no CPU fallback: without a usable CUDA device every compute call fails with
+ *     SS_ERR_DEVICE.
+ */
+#ifndef SNARK_SETUP_B200_H
+#define SNARK_SETUP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { SS_CURVE_BLS12_377 = 0, SS_CURVE_BW6_761 = 1 } ss_curve;
+typedef enum { SS_G1 = 0, SS_G2 = 1 } ss_group;
+
+/* setup_utils::CheckForCorrectness (setup-utils/src/elements.rs:18-23) */
+typedef enum { SS_CHECK_FULL = 0, SS_CHECK_ONLY_NON_ZERO = 1, SS_CHECK_ONLY_IN_GROUP = 2, SS_CHECK_NO = 3 } ss_check;
+/* setup_utils::SubgroupCheckMode (setup-utils/src/elements.rs:86-91) */
+typedef enum { SS_SUBGROUP_AUTO = 0, SS_SUBGROUP_DIRECT = 1, SS_SUBGROUP_BATCHED = 2, SS_SUBGROUP_NO = 3 } ss_subgroup_mode;
+/* phase1::ContributionMode / ProvingSystem (phase1/src/objects/parameters.rs) */
+typedef enum { SS_MODE_FULL = 0, SS_MODE_CHUNKED = 1 } ss_contribution_mode;
+typedef enum { SS_GROTH16 = 0, SS_MARLIN = 1 } ss_proving_system;
+
+typedef enum {
+    SS_OK = 0,
+    SS_ERR_INVALID_DATA = 1,       /* Error::ZexeSerializationError(InvalidData)      */
+    SS_ERR_UNEXPECTED_FLAGS = 2,   /* Error::ZexeSerializationError(UnexpectedFlags)  */
+    SS_ERR_POINT_AT_INFINITY = 3,  /* Error::PointAtInfinity                          */
+    SS_ERR_INCORRECT_SUBGROUP = 4, /* Error::IncorrectSubgroup                        */
+    SS_ERR_INVALID_LENGTH = 5,     /* Error::InvalidLength { expected, got }          */
+    SS_ERR_INVALID_CHUNK = 6,      /* Error::InvalidChunk                             */
+    SS_ERR_BATCH_TOO_SMALL = 7,    /* Error::BatchTooSmall                            */
+    SS_ERR_INVALID_ARGUMENT = 8,   /* (no reference equivalent: bad enum / null pointer)  */
+    SS_ERR_DEVICE = 9              /* CUDA failure; the Rust shim turns this into a panic */
+} ss_status;
+
+typedef struct {
+    int code;          /* ss_status */
+    uint64_t index;    /* element index the error refers to (lowest failing index), or 0 */
+    uint64_t expected; /* InvalidLength */
+    uint64_t got;      /* InvalidLength */
+    char message[160];
+} ss_error_info;
+
+/* -------------------------------------------------------------------------------------------- */
+/* device management                                                                            */
+/* -------------------------------------------------------------------------------------------- */
+/* Select the CUDA devices this process uses (n = 0: device 0, or $SNARK_SETUP_GPUS="0,1,.."). */
+int ss_init(const int* devices, int n_devices);
+void ss_shutdown(void);
+int ss_device_count(void);
+void ss_last_error(ss_error_info* out);
+const char* ss_version(void);
+
+/* buffer_size::<C>(compression) — setup-utils/src/io/mod.rs:13-15 */
+size_t ss_element_size(int curve, int group, int compressed);
+size_t ss_scalar_size(int curve);
+
+/* -------------------------------------------------------------------------------------------- */
+/* setup-utils helpers                                                                          */
+/* -------------------------------------------------------------------------------------------- */
+/* generate_powers_of_tau — setup-utils/src/helpers.rs:32-37.  out: (end-start) scalars. */
+int ss_generate_powers_of_tau(int curve, const uint8_t* tau, uint64_t start, uint64_t end, uint8_t* out);
+
+/* batch_exp — setup-utils/src/helpers.rs:75-140.  `bases`: n uncompressed elements, updated in
+ * place; `exps`: n_exps scalars (n_exps != n => SS_ERR_INVALID_LENGTH, helpers.rs:81-86);
+ * `coeff`: one scalar or NULL. */
+int ss_batch_exp(int curve, int group, uint8_t* bases, size_t n, const uint8_t* exps, size_t n_exps,
+                 const uint8_t* coeff);
+
+/* batch_mul — setup-utils/src/helpers.rs:56-59 (phase2 delta^-1 of the H and L queries,
+ * phase2/src/parameters.rs:294-296; phase2/src/chunked_groth16.rs:442-466). */
+int ss_batch_mul(int curve, int group, uint8_t* bases, size_t n, const uint8_t* coeff);
+
+/* read_batch + write_batch — setup-utils/src/io/read.rs:110-135, io/write.rs:57-66: decode n
+ * elements with the given validation and re-encode them (decompress_buffer,
+ * phase1/src/helpers/accumulator.rs:182-198, when in_compressed=1,out_compressed=0).
+ * out may be NULL to validate only. */
+int ss_transcode(int curve, int group, const uint8_t* in, int in_compressed, int check, uint8_t* out,
+                 int out_compressed, size_t n);
+
+/* check_subgroup — setup-utils/src/elements.rs:123-150 on n serialized elements. */
+int ss_check_subgroup(int curve, int group, const uint8_t* in, int compressed, size_t n, int subgroup_mode);
+
+/* -------------------------------------------------------------------------------------------- */
+/* phase1 helpers                                                                               */
+/* -------------------------------------------------------------------------------------------- */
+/* apply_powers — phase1/src/helpers/buffers.rs:77-97, fused with generate_powers_of_tau.
+ * in/out point at element `start` of the vector (the caller has applied start*size already);
+ * n = end - start.  Scalars: `powers` (n explicit scalars) when non-NULL, otherwise
+ * tau^(first_power + i).  `coeff` NULL or one scalar (alpha / beta). */
+int ss_apply_powers(int curve, int group, const uint8_t* in, int in_compressed, int in_check, uint8_t* out,
+                    int out_compressed, size_t n, const uint8_t* powers, const uint8_t* tau, uint64_t first_power,
+                    const uint8_t* coeff);
+
+/* Phase1Parameters — phase1/src/objects/parameters.rs:115-294 */
+typedef struct {
+    int curve;             /* ss_curve */
+    int proving_system;    /* ss_proving_system (only SS_GROTH16 is accelerated in this round) */
+    int contribution_mode; /* ss_contribution_mode */
+    uint64_t chunk_index;
+    uint64_t chunk_size;
+    uint32_t total_size_in_log2;
+    uint64_t batch_size;
+} ss_phase1_params;
+
+typedef struct {
+    uint64_t powers_length, powers_g1_length, g1_chunk_size, other_chunk_size;
+    uint64_t accumulator_size, contribution_size, public_key_size, hash_size;
+} ss_phase1_sizes;
+
+int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out);
+
+/* Phase1::computation — phase1/src/computation.rs:16-308 (Groth16 branch :40-193).
+ * input/output are the whole challenge / response buffers including the 64-byte hash prefix
+ * (which is not touched, as in the reference); tau/alpha/beta = PrivateKey scalars. */
+int ss_phase1_computation(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
+                          size_t output_len, int compressed_input, int compressed_output, int check_input,
+                          const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta);
+
+/* Same computation on buffers that already live in device memory of the current device
+ * (bench: throughput with inputs resident in HBM).  `stream` is a cudaStream_t. */
+int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, size_t input_len, void* d_output,
+                              size_t output_len, int compressed_input, int compressed_output, int check_input,
+                              const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNARK_SETUP_B200_H */

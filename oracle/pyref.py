@@ -1,0 +1,654 @@
+"""Pure-Python big-int restatement of the snark-setup batch-exponentiation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (snark-setup_b200/) may import this file;
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may.
+
+This is the *second*, independent restatement (the first is oracle/oracle.cpp, Montgomery / 64-bit
+limbs).  It uses nothing but Python integers and textbook affine formulas so that a disagreement
+with oracle.cpp or with the CUDA path points at an arithmetic bug rather than a shared mistake.
+
+PARITY UNPINNED: the reference (nimiq/snark-setup) holds no golden vectors for this path and its
+arithmetic lives in un-vendored arkworks 0.4 (ark-ff/ark-ec 0.4.2 @ paberr/algebra pb/0.4 1ab82cb7,
+ark-serialize 0.4.2, ark-bls12-377 / ark-bw6-761 0.4.0; /root/reference/Cargo.lock:80-82,103-105,
+151-153,187-189,459-461).  What is restated here is the published arkworks behaviour at the
+reference's call sites:
+
+  * generate_powers_of_tau      setup-utils/src/helpers.rs:32-37
+  * batch_exp / batch_mul       setup-utils/src/helpers.rs:56-59,75-140
+  * merge_pairs / power_pairs   setup-utils/src/helpers.rs:371-390
+  * read_batch / read_element   setup-utils/src/io/read.rs:57-73,110-135
+  * write_batch / write_element setup-utils/src/io/write.rs:30-67
+  * check_subgroup              setup-utils/src/elements.rs:123-150
+  * apply_powers                phase1/src/helpers/buffers.rs:77-97
+  * iter_chunk                  phase1/src/helpers/buffers.rs:22-73
+  * Phase1Parameters sizes      phase1/src/objects/parameters.rs:115-294
+  * Phase1::computation         phase1/src/computation.rs:16-193 (Groth16 branch)
+"""
+from __future__ import annotations
+
+# ----------------------------------------------------------------------------------------------
+# error codes (mirror setup_utils::Error, setup-utils/src/errors.rs:11-38)
+# ----------------------------------------------------------------------------------------------
+class SetupError(Exception):
+    pass
+
+
+class InvalidData(SetupError):          # ZexeSerializationError(InvalidData)
+    pass
+
+
+class UnexpectedFlags(SetupError):      # ZexeSerializationError(UnexpectedFlags)
+    pass
+
+
+class PointAtInfinity(SetupError):      # Error::PointAtInfinity
+    pass
+
+
+class IncorrectSubgroup(SetupError):    # Error::IncorrectSubgroup
+    pass
+
+
+class InvalidLength(SetupError):        # Error::InvalidLength
+    pass
+
+
+# CheckForCorrectness (setup-utils/src/elements.rs:18-23)
+FULL, ONLY_NON_ZERO, ONLY_IN_GROUP, NO = 0, 1, 2, 3
+
+
+# ----------------------------------------------------------------------------------------------
+# fields
+# ----------------------------------------------------------------------------------------------
+class Fp:
+    """Prime field; elements are Python ints in [0, p)."""
+
+    def __init__(self, p: int):
+        self.p = p
+        self.bits = p.bit_length()
+        self.degree = 1
+        # two-adicity data for Tonelli-Shanks
+        s, t = 0, p - 1
+        while t % 2 == 0:
+            s += 1
+            t //= 2
+        self.two_adicity, self.t = s, t
+        z = 2
+        while pow(z, (p - 1) // 2, p) != p - 1:
+            z += 1
+        self.qnr = z
+
+    zero = 0
+    one = 1
+
+    def add(self, a, b): return (a + b) % self.p
+    def sub(self, a, b): return (a - b) % self.p
+    def neg(self, a): return (-a) % self.p
+    def mul(self, a, b): return (a * b) % self.p
+    def sqr(self, a): return (a * a) % self.p
+    def inv(self, a): return pow(a, self.p - 2, self.p)
+    def is_zero(self, a): return a == 0
+    def from_int(self, v): return v % self.p
+
+    def sqrt(self, a):
+        """Any square root or None."""
+        p = self.p
+        if a == 0:
+            return 0
+        if pow(a, (p - 1) // 2, p) != 1:
+            return None
+        if p % 4 == 3:
+            return pow(a, (p + 1) // 4, p)
+        # Tonelli-Shanks
+        s, t = self.two_adicity, self.t
+        z = pow(self.qnr, t, p)
+        w = pow(a, (t - 1) // 2, p)
+        x = a * w % p
+        b = x * w % p
+        v = s
+        while b != 1:
+            k, b2k = 0, b
+            while b2k != 1:
+                b2k = b2k * b2k % p
+                k += 1
+            wj = z
+            for _ in range(v - k - 1):
+                wj = wj * wj % p
+            z = wj * wj % p
+            b = b * z % p
+            x = x * wj % p
+            v = k
+        return x
+
+    def gt(self, a, b):
+        """a > b as canonical integers."""
+        return a > b
+
+    # canonical little-endian bytes, ceil((bits + flag_bits)/8) long (ark-ff Fp serialize_with_flags)
+    def size(self, flag_bits=0):
+        return (self.bits + flag_bits + 7) // 8
+
+    def to_bytes(self, a, flags=0, flag_bits=0):
+        b = bytearray(a.to_bytes(self.size(flag_bits), "little"))
+        b[-1] |= flags
+        return bytes(b)
+
+    def from_bytes(self, b, flag_bits=0):
+        """Returns (element, flags_byte). Raises InvalidData for non-canonical values."""
+        b = bytearray(b)
+        assert len(b) == self.size(flag_bits)
+        flags = 0
+        if flag_bits:
+            mask = (0xFF << (8 - flag_bits)) & 0xFF
+            flags = b[-1] & mask
+            b[-1] &= ~mask & 0xFF
+            if flag_bits == 2 and flags == 0xC0:
+                raise UnexpectedFlags()
+        v = int.from_bytes(b, "little")
+        if v >= self.p:
+            raise InvalidData("field element >= modulus")
+        return v, flags
+
+
+class Fp2:
+    """Fp[u]/(u^2 - nr); elements are (c0, c1)."""
+
+    def __init__(self, base: Fp, nr: int):
+        self.b = base
+        self.p = base.p
+        self.nr = nr % base.p
+        self.degree = 2
+
+    zero = (0, 0)
+    one = (1, 0)
+
+    def add(self, a, b): return ((a[0] + b[0]) % self.p, (a[1] + b[1]) % self.p)
+    def sub(self, a, b): return ((a[0] - b[0]) % self.p, (a[1] - b[1]) % self.p)
+    def neg(self, a): return ((-a[0]) % self.p, (-a[1]) % self.p)
+
+    def mul(self, a, b):
+        p = self.p
+        return ((a[0] * b[0] + self.nr * a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
+
+    def sqr(self, a): return self.mul(a, a)
+
+    def inv(self, a):
+        p = self.p
+        n = (a[0] * a[0] - self.nr * a[1] * a[1]) % p
+        ni = pow(n, p - 2, p)
+        return (a[0] * ni % p, (-a[1]) * ni % p)
+
+    def is_zero(self, a): return a[0] == 0 and a[1] == 0
+    def from_int(self, v): return (v % self.p, 0)
+
+    def sqrt(self, a):
+        p, F = self.p, self.b
+        if a[1] == 0:
+            r = F.sqrt(a[0])
+            if r is not None:
+                return (r, 0)
+            # a0 is a non-residue in Fp: sqrt is purely imaginary: (c1 u)^2 = c1^2 nr = a0
+            r = F.sqrt(a[0] * pow(self.nr, p - 2, p) % p)
+            return None if r is None else (0, r)
+        norm = (a[0] * a[0] - self.nr * a[1] * a[1]) % p
+        alpha = F.sqrt(norm)
+        if alpha is None:
+            return None
+        half = pow(2, p - 2, p)
+        delta = (a[0] + alpha) * half % p
+        c0 = F.sqrt(delta)
+        if c0 is None:
+            delta = (a[0] - alpha) * half % p
+            c0 = F.sqrt(delta)
+            if c0 is None:
+                return None
+        c1 = a[1] * pow(2 * c0, p - 2, p) % p
+        r = (c0, c1)
+        assert self.sqr(r) == (a[0] % p, a[1] % p)
+        return r
+
+    def gt(self, a, b):
+        """Lexicographic, c1 first then c0 (ark-ff QuadExtField Ord)."""
+        if a[1] != b[1]:
+            return a[1] > b[1]
+        return a[0] > b[0]
+
+    def size(self, flag_bits=0):
+        return self.b.size(0) + self.b.size(flag_bits)
+
+    def to_bytes(self, a, flags=0, flag_bits=0):
+        return self.b.to_bytes(a[0]) + self.b.to_bytes(a[1], flags, flag_bits)
+
+    def from_bytes(self, b, flag_bits=0):
+        n0 = self.b.size(0)
+        c0, _ = self.b.from_bytes(b[:n0], 0)
+        c1, flags = self.b.from_bytes(b[n0:], flag_bits)
+        return (c0, c1), flags
+
+
+# ----------------------------------------------------------------------------------------------
+# short-Weierstrass groups, a = 0
+# ----------------------------------------------------------------------------------------------
+FLAG_NEG = 0x80   # SWFlags::YIsNegative
+FLAG_INF = 0x40   # SWFlags::PointAtInfinity
+
+
+class Group:
+    """y^2 = x^3 + b over field F (a = 0). Points: None (identity) or (x, y)."""
+
+    def __init__(self, name, F, b, gen, r):
+        self.name, self.F, self.b, self.gen, self.r = name, F, b, gen, r
+        self.usize = 2 * F.size(0) if F.degree == 1 else F.size(0) + F.size(2)
+        self.usize = F.size(0) + F.size(2)
+        self.csize = F.size(2)
+
+    # -- group law (affine, textbook) --
+    def on_curve(self, P):
+        if P is None:
+            return True
+        F = self.F
+        x, y = P
+        return F.sqr(y) == F.add(F.mul(F.sqr(x), x), self.b)
+
+    def neg(self, P):
+        return None if P is None else (P[0], self.F.neg(P[1]))
+
+    def add(self, P, Q):
+        F = self.F
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        if P[0] == Q[0]:
+            if P[1] == Q[1]:
+                if F.is_zero(P[1]):
+                    return None
+                x2 = F.sqr(P[0])
+                lam = F.mul(F.add(F.add(x2, x2), x2), F.inv(F.add(P[1], P[1])))
+            else:
+                return None
+        else:
+            lam = F.mul(F.sub(Q[1], P[1]), F.inv(F.sub(Q[0], P[0])))
+        x3 = F.sub(F.sub(F.sqr(lam), P[0]), Q[0])
+        y3 = F.sub(F.mul(lam, F.sub(P[0], x3)), P[1])
+        return (x3, y3)
+
+    def mul(self, P, k):
+        """k * P for a non-negative integer k (not reduced: callers decide)."""
+        # Jacobian double-and-add for speed; affine result.
+        if P is None or k == 0:
+            return None
+        F = self.F
+        X, Y, Z = P[0], P[1], F.one
+        inf = True
+        AX = AY = AZ = None
+        for bit in bin(k)[2:]:
+            if not inf:
+                AX, AY, AZ = self._jdbl(AX, AY, AZ)
+            if bit == "1":
+                if inf:
+                    AX, AY, AZ, inf = X, Y, Z, False
+                else:
+                    AX, AY, AZ = self._jadd_affine(AX, AY, AZ, P)
+                    if AX is None:
+                        inf = True
+        if inf:
+            return None
+        return self._to_affine(AX, AY, AZ)
+
+    def _to_affine(self, X, Y, Z):
+        F = self.F
+        if F.is_zero(Z):
+            return None
+        zi = F.inv(Z)
+        zi2 = F.sqr(zi)
+        return (F.mul(X, zi2), F.mul(Y, F.mul(zi2, zi)))
+
+    def _jdbl(self, X, Y, Z):
+        F = self.F
+        if F.is_zero(Z) or F.is_zero(Y):
+            return (F.one, F.one, F.zero)
+        A = F.sqr(X)
+        B = F.sqr(Y)
+        C = F.sqr(B)
+        t = F.sub(F.sub(F.sqr(F.add(X, B)), A), C)
+        D = F.add(t, t)
+        E = F.add(F.add(A, A), A)
+        Fv = F.sqr(E)
+        X3 = F.sub(Fv, F.add(D, D))
+        C8 = F.add(C, C); C8 = F.add(C8, C8); C8 = F.add(C8, C8)
+        Y3 = F.sub(F.mul(E, F.sub(D, X3)), C8)
+        Z3 = F.mul(F.add(Y, Y), Z)
+        return (X3, Y3, Z3)
+
+    def _jadd_affine(self, X1, Y1, Z1, Q):
+        """Jacobian + affine; returns (None,None,None) for identity result."""
+        F = self.F
+        if F.is_zero(Z1):
+            return (Q[0], Q[1], F.one)
+        Z1Z1 = F.sqr(Z1)
+        U2 = F.mul(Q[0], Z1Z1)
+        S2 = F.mul(F.mul(Q[1], Z1), Z1Z1)
+        if U2 == X1:
+            if S2 == Y1:
+                return self._jdbl(X1, Y1, Z1)
+            return (None, None, None)
+        H = F.sub(U2, X1)
+        R = F.sub(S2, Y1)
+        HH = F.sqr(H)
+        HHH = F.mul(H, HH)
+        V = F.mul(X1, HH)
+        X3 = F.sub(F.sub(F.sqr(R), HHH), F.add(V, V))
+        Y3 = F.sub(F.mul(R, F.sub(V, X3)), F.mul(Y1, HHH))
+        Z3 = F.mul(Z1, H)
+        return (X3, Y3, Z3)
+
+    def in_subgroup(self, P):
+        """p.mul_bigint(r).is_zero()  (setup-utils/src/elements.rs:138-142)."""
+        return self.mul(P, self.r) is None
+
+    # -- canonical serialisation (ark-ec 0.4 SWCurveConfig::{serialize,deserialize}_with_mode) --
+    def size(self, compressed):
+        return self.csize if compressed else self.usize
+
+    def flags_of(self, P):
+        if P is None:
+            return FLAG_INF
+        F = self.F
+        y = P[1]
+        return FLAG_NEG if F.gt(y, F.neg(y)) else 0
+
+    def encode(self, P, compressed):
+        F = self.F
+        fl = self.flags_of(P)
+        x, y = (F.zero, F.zero) if P is None else P
+        if compressed:
+            return F.to_bytes(x, fl, 2)
+        return F.to_bytes(x) + F.to_bytes(y, fl, 2)
+
+    def decode(self, b, compressed, check=NO):
+        """read_element (setup-utils/src/io/read.rs:57-73) for one element."""
+        F = self.F
+        validate = check in (FULL, ONLY_IN_GROUP)
+        if compressed:
+            x, fl = F.from_bytes(b, 2)
+            if fl == (FLAG_NEG | FLAG_INF):
+                raise UnexpectedFlags()
+            if fl & FLAG_INF:
+                P = None
+            else:
+                y = F.sqrt(F.add(F.mul(F.sqr(x), x), self.b))
+                if y is None:
+                    raise InvalidData("x^3+b is not a square")
+                ny = F.neg(y)
+                lo, hi = (y, ny) if F.gt(ny, y) else (ny, y)
+                P = (x, hi if fl & FLAG_NEG else lo)
+        else:
+            nx = F.size(0)
+            x, _ = F.from_bytes(b[:nx], 0)
+            y, fl = F.from_bytes(b[nx:], 2)
+            if fl == (FLAG_NEG | FLAG_INF):
+                raise UnexpectedFlags()
+            P = None if fl & FLAG_INF else (x, y)
+        if P is not None and validate:
+            if not self.on_curve(P) or not self.in_subgroup(P):
+                raise InvalidData("point failed Validate::Yes")
+        if check in (FULL, ONLY_NON_ZERO) and P is None:
+            raise PointAtInfinity()
+        return P
+
+    # -- batches --
+    def read_batch(self, buf, compressed, check=NO):
+        sz = self.size(compressed)
+        assert len(buf) % sz == 0
+        return [self.decode(buf[i:i + sz], compressed, check) for i in range(0, len(buf), sz)]
+
+    def write_batch(self, pts, compressed):
+        return b"".join(self.encode(P, compressed) for P in pts)
+
+
+class Curve:
+    def __init__(self, name, g1: Group, g2: Group, r: int):
+        self.name, self.g1, self.g2, self.r = name, g1, g2, r
+        self.fr = Fp(r)
+        self.fr_size = (r.bit_length() + 7) // 8
+
+
+# ----------------------------------------------------------------------------------------------
+# curve constants (re-verified by tests/test_pyref.py: on-curve, r*G = O)
+# ----------------------------------------------------------------------------------------------
+BLS12_377_Q = 0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001
+BLS12_377_R = 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001
+BW6_761_Q = 0x122e824fb83ce0ad187c94004faff3eb926186a81d14688528275ef8087be41707ba638e584e91903cebaff25b423048689c8ed12f9fd9071dcd3dc73ebff2e98a116c25667a8f8160cf8aeeaf0a437e6913e6870000082f49d00000000008b
+
+
+def _mk_bls12_377():
+    fq = Fp(BLS12_377_Q)
+    fq2 = Fp2(fq, -5)
+    g1 = Group("bls12_377.g1", fq, 1,
+               (0x008848defe740a67c8fc6225bf87ff5485951e2caa9d41bb188282c8bd37cb5cd5481512ffcd394eeab9b16eb21be9ef,
+                0x01914a69c5102eff1f674f5d30afeec4bd7fb348ca3e52d96d182ad44fb82305c2fe3d3634a9591afd82de55559c8ea6),
+               BLS12_377_R)
+    g2 = Group("bls12_377.g2", fq2,
+               (0, 155198655607781456406391640216936120121836107652948796323930557600032281009004493664981332883744016074664192874906),
+               ((233578398248691099356572568220835526895379068987715365179118596935057653620464273615301663571204657964920925606294,
+                 140913150380207355837477652521042157274541796891053068589147167627541651775299824604154852141315666357241556069118),
+                (63160294768292073209381361943935198908131692476676907196754037919244929611450776219210369229519898517858833747423,
+                 149157405641012693445398062341192467754805999074082136895788947234480009303640899064710353187729182149407503257491)),
+               BLS12_377_R)
+    return Curve("bls12_377", g1, g2, BLS12_377_R)
+
+
+def _mk_bw6_761():
+    fq = Fp(BW6_761_Q)
+    g1 = Group("bw6_761.g1", fq, BW6_761_Q - 1,
+               (0x01075b020ea190c8b277ce98a477beaee6a0cfb7551b27f0ee05c54b85f56fc779017ffac15520ac11dbfcd294c2e746a17a54ce47729b905bd71fa0c9ea097103758f9a280ca27f6750dd0356133e82055928aca6af603f4088f3af66e5b43d,
+                0x0058b84e0a6fc574e6fd637b45cc2a420f952589884c9ec61a7348d2a2e573a3265909f1af7e0dbac5b8fa1771b5b806cc685d31717a4c55be3fb90b6fc2cdd49f9df141b3053253b2b08119cad0fb93ad1cb2be0b20d2a1bafc8f2db4e95363),
+               BLS12_377_Q)
+    g2 = Group("bw6_761.g2", fq, 4,
+               (0x0110133241d9b816c852a82e69d660f9d61053aac5a7115f4c06201013890f6d26b41c5dab3da268734ec3f1f09feb58c5bbcae9ac70e7c7963317a300e1b6bace6948cb3cd208d700e96efbc2ad54b06410cf4fe1bf995ba830c194cd025f1c,
+                0x0017c3357761369f8179eb10e4b6d2dc26b7cf9acec2181c81a78e2753ffe3160a1d86c80b95a59c94c97eb733293fef64f293dbd2c712b88906c170ffa823003ea96fcd504affc758aa2d3a3c5a02a591ec0594f9eac689eb70a16728c73b61),
+               BLS12_377_Q)
+    return Curve("bw6_761", g1, g2, BLS12_377_Q)
+
+
+BLS12_377 = _mk_bls12_377()
+BW6_761 = _mk_bw6_761()
+CURVES = {"bls12_377": BLS12_377, "bw6_761": BW6_761}
+
+
+# ----------------------------------------------------------------------------------------------
+# the hot path
+# ----------------------------------------------------------------------------------------------
+def generate_powers_of_tau(curve: Curve, tau: int, start: int, end: int):
+    """setup-utils/src/helpers.rs:32-37 — each power independently as tau.pow([i])."""
+    return [pow(tau, i, curve.r) for i in range(start, end)]
+
+
+def batch_exp(group: Group, bases, exps, coeff=None):
+    """setup-utils/src/helpers.rs:75-140: bases[i] <- (exps[i]*coeff?) * bases[i], affine."""
+    if len(bases) != len(exps):
+        raise InvalidLength(f"expected {len(bases)} got {len(exps)}")
+    r = group.r
+    out = []
+    for P, e in zip(bases, exps):
+        if coeff is not None:
+            e = e * coeff % r
+        out.append(group.mul(P, e % r))
+    return out
+
+
+def batch_mul(group: Group, bases, coeff):
+    """setup-utils/src/helpers.rs:56-59."""
+    return batch_exp(group, bases, [coeff] * len(bases))
+
+
+def apply_powers(group: Group, inp, in_compressed, in_check, out_compressed, start, end, powers, coeff=None):
+    """phase1/src/helpers/buffers.rs:77-97. Returns the bytes for output[start*out_sz .. end*out_sz]."""
+    isz = group.size(in_compressed)
+    elems = group.read_batch(inp[start * isz:end * isz], in_compressed, in_check)
+    elems = batch_exp(group, elems, powers[:end - start], coeff)
+    return group.write_batch(elems, out_compressed)
+
+
+def msm(group: Group, pts, scalars):
+    acc = None
+    for P, k in zip(pts, scalars):
+        acc = group.add(acc, group.mul(P, k % group.r))
+    return acc
+
+
+def merge_pairs(group: Group, v1, v2, rho):
+    """setup-utils/src/helpers.rs:371-384 with the randomness made explicit."""
+    assert len(v1) == len(v2) == len(rho)
+    return msm(group, v1, rho), msm(group, v2, rho)
+
+
+def power_pairs(group: Group, v, rho):
+    """setup-utils/src/helpers.rs:388-390."""
+    return merge_pairs(group, v[:-1], v[1:], rho)
+
+
+def check_subgroup(group: Group, pts):
+    """setup-utils/src/elements.rs:123-150 (all modes but `No` collapse to the direct loop)."""
+    if not all(group.in_subgroup(P) for P in pts):
+        raise IncorrectSubgroup()
+
+
+# ----------------------------------------------------------------------------------------------
+# phase1 layout + schedule
+# ----------------------------------------------------------------------------------------------
+FULL_MODE, CHUNKED_MODE = 0, 1
+GROTH16, MARLIN = 0, 1
+
+
+class Phase1Parameters:
+    """phase1/src/objects/parameters.rs:115-294."""
+
+    def __init__(self, curve: Curve, power: int, batch_size: int, mode=FULL_MODE, chunk_index=0, chunk_size=0,
+                 proving_system=GROTH16):
+        self.curve, self.total_size_in_log2, self.batch_size = curve, power, batch_size
+        self.contribution_mode, self.chunk_index, self.chunk_size = mode, chunk_index, chunk_size
+        self.proving_system = proving_system
+        self.hash_size = 64
+        self.powers_length = 1 << power
+        self.powers_g1_length = (self.powers_length << 1) - 1
+        upper = self.powers_g1_length if proving_system == GROTH16 else self.powers_length
+        if mode == CHUNKED_MODE:
+            start, end = chunk_index * chunk_size, (chunk_index + 1) * chunk_size
+        else:
+            start, end = 0, upper
+        self.g1_chunk_size = upper - start if end > upper else end - start
+        if proving_system == GROTH16:
+            pl = self.powers_length
+            if end > pl and start >= pl:
+                self.other_chunk_size = 0
+            elif end > pl:
+                self.other_chunk_size = pl - start
+            else:
+                self.other_chunk_size = end - start
+        else:
+            self.other_chunk_size = 0
+        g1u, g2u = curve.g1.usize, curve.g2.usize
+        g1c, g2c = curve.g1.csize, curve.g2.csize
+        self.public_key_size = 3 * g2c + 6 * g1c
+        if proving_system == GROTH16:
+            self.accumulator_size = (self.g1_chunk_size * g1u + self.other_chunk_size * (g2u + 2 * g1u) + g2u
+                                     + self.hash_size)
+            self.contribution_size = (self.g1_chunk_size * g1c + self.other_chunk_size * (g2c + 2 * g1c) + g2c
+                                      + self.hash_size + self.public_key_size)
+        else:
+            extra_u = extra_c = 0
+            if chunk_index == 0:
+                extra_u = 3 * g1u + 3 * power * g1u + (power + 2) * g2u
+                extra_c = 3 * g1c + 3 * power * g1c + (power + 2) * g2c
+            self.accumulator_size = self.g1_chunk_size * g1u + extra_u + self.hash_size
+            self.contribution_size = self.g1_chunk_size * g1c + extra_c + self.hash_size + self.public_key_size
+
+    def get_length(self, compressed):
+        return self.contribution_size - self.public_key_size if compressed else self.accumulator_size
+
+    def split_offsets(self, compressed):
+        """(offset, count, element_size) of [TauG1, TauG2, AlphaG1, BetaG1, BetaG2] (buffers.rs:293-341), Groth16."""
+        assert self.proving_system == GROTH16
+        g1, g2 = self.curve.g1.size(compressed), self.curve.g2.size(compressed)
+        o = self.hash_size
+        out = []
+        for cnt, sz in ((self.g1_chunk_size, g1), (self.other_chunk_size, g2), (self.other_chunk_size, g1),
+                        (self.other_chunk_size, g1), (1, g2)):
+            out.append((o, cnt, sz))
+            o += cnt * sz
+        return out
+
+
+def iter_chunk(params: Phase1Parameters):
+    """phase1/src/helpers/buffers.rs:22-73 — list of (start, end) windows, overlapping by one element."""
+    upper = params.powers_g1_length if params.proving_system == GROTH16 else params.powers_length
+    if params.contribution_mode == CHUNKED_MODE:
+        lo, hi = params.chunk_index * params.chunk_size, min((params.chunk_index + 1) * params.chunk_size, upper)
+    else:
+        lo, hi = 0, upper
+    step = params.batch_size - 1
+    out = []
+    i = lo
+    while i < hi:
+        chunk = list(range(i, min(i + step, hi)))
+        if len(chunk) >= 2:
+            start, end = chunk[0], chunk[-1]
+            out.append((start, end + 1 if end >= hi - 1 else end + 2))
+        else:
+            start = chunk[0]
+            if start >= hi - 1:
+                if hi == lo + 1:
+                    out.append((start, start + 1))
+            else:
+                out.append((start, start + 2))
+        i += step
+    return out
+
+
+def phase1_computation(params: Phase1Parameters, inp: bytes, compressed_in, compressed_out, check_in,
+                       tau: int, alpha: int, beta: int) -> bytearray:
+    """Phase1::computation, Groth16 branch (phase1/src/computation.rs:16-193).
+
+    Returns a buffer of params.get_length(compressed_out) bytes whose first 64 bytes (hash) are left zero:
+    the caller writes the hash (phase1-cli/src/contribute.rs:92-96)."""
+    cv = params.curve
+    out = bytearray(params.get_length(compressed_out))
+    si = params.split_offsets(compressed_in)
+    so = params.split_offsets(compressed_out)
+    views_in = [inp[o:o + c * s] for (o, c, s) in si]
+
+    def put(vec, start, data):
+        o, _, s = so[vec]
+        out[o + start * s:o + start * s + len(data)] = data
+
+    # beta_g2 (computation.rs:42-50)
+    P = cv.g2.decode(views_in[4], compressed_in, check_in)
+    put(4, 0, cv.g2.encode(cv.g2.mul(P, beta % cv.r), compressed_out))
+    off = params.chunk_index * params.chunk_size if params.contribution_mode == CHUNKED_MODE else 0
+    for (start, end) in iter_chunk(params):
+        powers = generate_powers_of_tau(cv, tau, start, end)
+        put(0, start - off, apply_powers(cv.g1, views_in[0], compressed_in, check_in, compressed_out,
+                                         start - off, end - off, powers))
+        if start < params.powers_length:
+            if params.contribution_mode == CHUNKED_MODE:
+                mx = min((params.chunk_index + 1) * params.chunk_size, params.powers_length)
+            else:
+                mx = params.powers_length
+            e2 = mx if start + params.batch_size > mx else end
+            s, e = start - off, e2 - off
+            put(1, s, apply_powers(cv.g2, views_in[1], compressed_in, check_in, compressed_out, s, e, powers))
+            put(2, s, apply_powers(cv.g1, views_in[2], compressed_in, check_in, compressed_out, s, e, powers, alpha))
+            put(3, s, apply_powers(cv.g1, views_in[3], compressed_in, check_in, compressed_out, s, e, powers, beta))
+    return out
+
+
+def phase1_initialization(params: Phase1Parameters, compressed) -> bytearray:
+    """Phase1::initialization (phase1/src/initialization.rs:12-57): every slot holds the generator."""
+    cv = params.curve
+    out = bytearray(params.get_length(compressed))
+    for vec, (o, c, s) in enumerate(params.split_offsets(compressed)):
+        g = cv.g2 if vec in (1, 4) else cv.g1
+        out[o:o + c * s] = g.encode(g.gen, compressed) * c
+    return out

@@ -1,0 +1,668 @@
+// C ABI (include/snark_setup_b200.h) and the host-side driver of the batch-exponentiation path.
+//
+// Host logic mirrors, in C++, the orchestration the reference keeps in Rust:
+//   Phase1Parameters::new / chunk_sizes   phase1/src/objects/parameters.rs:115-294
+//   split / split_mut                     phase1/src/helpers/buffers.rs:246-341
+//   apply_powers                          phase1/src/helpers/buffers.rs:77-97
+//   Phase1::computation (Groth16)         phase1/src/computation.rs:40-193
+// The reference walks each vector in `batch_size` windows on rayon threads; results do not depend
+// on the windowing, so here each vector is cut into device tiles (default 2^18 elements) that are
+// pipelined over two CUDA streams: H2D of tile k+1 overlaps the kernels of tile k.
+#ifndef __CUDACC__
+#error "api.cu is the CUDA product path and must be built with nvcc (no CPU fallback exists)"
+#endif
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/snark_setup_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+using namespace ss;
+
+thread_local ss_error_info g_err = {0, 0, 0, 0, {0}};
+
+int fail(int code, uint64_t index, uint64_t expected, uint64_t got, const char* fmt, ...) {
+    g_err.code = code;
+    g_err.index = index;
+    g_err.expected = expected;
+    g_err.got = got;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err.message, sizeof(g_err.message), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(SS_ERR_DEVICE, 0, 0, 0, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                           \
+    } while (0)
+
+const GroupOps* group_ops(int curve, int group) {
+    if (curve == SS_CURVE_BLS12_377) return group == SS_G1 ? &ops_bls377_g1() : group == SS_G2 ? &ops_bls377_g2() : nullptr;
+    if (curve == SS_CURVE_BW6_761) return group == SS_G1 ? &ops_bw6_g1() : group == SS_G2 ? &ops_bw6_g2() : nullptr;
+    return nullptr;
+}
+
+// ---- devices ------------------------------------------------------------------------------------
+std::mutex g_mu;
+std::vector<int> g_devices;
+bool g_inited = false;
+
+int ensure_init() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return SS_OK;
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+        return fail(SS_ERR_DEVICE, 0, 0, 0, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (g_devices.empty()) {
+        const char* env = getenv("SNARK_SETUP_GPUS");
+        if (env && *env) {
+            std::string s(env);
+            size_t pos = 0;
+            while (pos < s.size()) {
+                size_t c = s.find(',', pos);
+                if (c == std::string::npos) c = s.size();
+                g_devices.push_back(atoi(s.substr(pos, c - pos).c_str()));
+                pos = c + 1;
+            }
+        } else {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            g_devices.push_back(cur);
+        }
+    }
+    for (int d : g_devices)
+        if (d < 0 || d >= cnt) return fail(SS_ERR_DEVICE, 0, 0, 0, "device %d out of range (count %d)", d, cnt);
+    g_inited = true;
+    return SS_OK;
+}
+
+// ---- lanes: stream + scratch, cached across calls -------------------------------------------------
+struct Lane {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    uint8_t* buf = nullptr;  // one slab, carved per use
+    size_t cap = 0;
+    bool busy = false;
+};
+std::vector<Lane*> g_lanes;
+
+size_t tile_elems() {
+    static size_t t = [] {
+        const char* e = getenv("SS_TILE_LOG2");
+        int l = e ? atoi(e) : 18;
+        if (l < 8) l = 8;
+        if (l > 24) l = 24;
+        return (size_t)1 << l;
+    }();
+    return t;
+}
+
+int lane_acquire(int device, size_t bytes, Lane** out) {
+    Lane* ln = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (Lane* l : g_lanes)
+            if (!l->busy && l->device == device) {
+                ln = l;
+                break;
+            }
+        if (!ln) {
+            ln = new Lane();
+            ln->device = device;
+            g_lanes.push_back(ln);
+        }
+        ln->busy = true;
+    }
+    CU(cudaSetDevice(device));
+    if (!ln->stream) CU(cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
+    if (ln->cap < bytes) {
+        if (ln->buf) CU(cudaFree(ln->buf));
+        ln->buf = nullptr;
+        ln->cap = 0;
+        CU(cudaMalloc(&ln->buf, bytes));
+        ln->cap = bytes;
+    }
+    *out = ln;
+    return SS_OK;
+}
+
+void lane_release(Lane* l) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    l->busy = false;
+}
+
+struct LaneGuard {
+    Lane* l = nullptr;
+    ~LaneGuard() {
+        if (l) lane_release(l);
+    }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// carve helper
+struct Carver {
+    uint8_t* p;
+    size_t off = 0;
+    explicit Carver(uint8_t* base) : p(base) {}
+    template <class T>
+    T* take(size_t bytes) {
+        T* r = reinterpret_cast<T*>(p + off);
+        off += align_up(bytes, 256);
+        return r;
+    }
+};
+
+// scratch a tile of `t` elements needs (besides staged in/out bytes)
+size_t scratch_bytes(const GroupOps& o, size_t t) {
+    return align_up((size_t)3 * o.coord_words * 4 * t, 256) + align_up((size_t)o.coord_words * 4 * t, 256) +
+           align_up((size_t)2 * o.coord_words * 4 * t, 256) + align_up(t, 256);
+}
+
+int decode_status(unsigned long long st, uint64_t base, const char* what) {
+    if (st == STATUS_OK) return SS_OK;
+    int code = (int)(st & 0xff);
+    uint64_t idx = base + (st >> 8);
+    return fail(code, idx, 0, 0, "%s: element %llu: error %d", what, (unsigned long long)idx, code);
+}
+
+uint32_t normalize_threads(uint64_t n) {
+    // each thread batch-inverts up to 32 elements; at least one element per thread
+    uint64_t t = (n + 31) / 32;
+    if (t < 1024) t = std::min<uint64_t>(n, 1024);
+    return (uint32_t)t;
+}
+
+// ---- scalar set-up shared by the vectors of one call ----------------------------------------------
+struct ScalarCtx {
+    uint32_t* d_tab = nullptr;      // [64][frw]
+    uint32_t* d_coeff[3] = {};      // Montgomery coefficients (slot 0 = "one")
+};
+
+// One vector of `n` elements.  host==true: in/out are host pointers and are staged tile by tile;
+// host==false: in/out are device pointers of `device`.
+struct VectorJob {
+    const GroupOps* ops;
+    const uint8_t* in;
+    uint8_t* out;
+    int in_c, out_c, check;
+    uint64_t n;
+    const uint8_t* exps;   // explicit scalars (host or device like in/out) or null
+    const uint32_t* d_tab;
+    uint64_t first_power;
+    const uint32_t* d_coeff_m;
+    int has_coeff;
+    const char* what;
+};
+
+int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_stream) {
+    if (j.n == 0) return SS_OK;
+    const GroupOps& o = *j.ops;
+    const size_t isz = j.in_c ? o.csize : o.usize, osz = j.out_c ? o.csize : o.usize;
+    const size_t T = std::min<uint64_t>(tile_elems(), j.n);
+    const size_t ntiles = (j.n + T - 1) / T;
+    const int nl = (host && ntiles > 1) ? 2 : 1;
+    size_t per_lane = scratch_bytes(o, T) + 256;
+    if (host) per_lane += align_up(isz * T, 256) + align_up(osz * T, 256) + (j.exps ? align_up((size_t)o.fr_bytes * T, 256) : 0);
+    LaneGuard lg[2];
+    for (int k = 0; k < nl; k++) {
+        int rc = lane_acquire(device, per_lane + ntiles * 8 + 256, &lg[k].l);
+        if (rc) return rc;
+    }
+    std::vector<unsigned long long> st(ntiles, STATUS_OK);
+    // status words live at the head of lane 0's slab
+    unsigned long long* d_status = reinterpret_cast<unsigned long long*>(lg[0].l->buf);
+    cudaStream_t s0 = (!host && user_stream) ? user_stream : lg[0].l->stream;
+    CU(cudaMemsetAsync(d_status, 0xff, ntiles * 8, s0));
+    cudaEvent_t ev_init = nullptr;
+    if (nl > 1) {
+        CU(cudaEventCreateWithFlags(&ev_init, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev_init, s0));
+        CU(cudaStreamWaitEvent(lg[1].l->stream, ev_init, 0));
+    }
+    const size_t status_bytes = align_up(ntiles * 8, 256);
+    int rc = SS_OK;
+    for (size_t t = 0; t < ntiles; t++) {
+        const uint64_t e0 = t * T, cnt = std::min<uint64_t>(T, j.n - e0);
+        Lane* ln = lg[t % nl].l;
+        cudaStream_t s = (!host && user_stream) ? user_stream : ln->stream;
+        Carver cv(ln->buf + ((t % nl) == 0 ? status_bytes : 0));
+        uint32_t* jac = cv.take<uint32_t>((size_t)3 * o.coord_words * 4 * T);
+        uint32_t* prefix = cv.take<uint32_t>((size_t)o.coord_words * 4 * T);
+        uint32_t* aff = cv.take<uint32_t>((size_t)2 * o.coord_words * 4 * T);
+        uint8_t* inf = cv.take<uint8_t>(T);
+        const uint8_t* d_in;
+        uint8_t* d_out;
+        const uint8_t* d_exps = nullptr;
+        if (host) {
+            uint8_t* bi = cv.take<uint8_t>(isz * T);
+            uint8_t* bo = cv.take<uint8_t>(osz * T);
+            CU(cudaMemcpyAsync(bi, j.in + e0 * isz, cnt * isz, cudaMemcpyHostToDevice, s));
+            if (j.exps) {
+                uint8_t* be = cv.take<uint8_t>((size_t)o.fr_bytes * T);
+                CU(cudaMemcpyAsync(be, j.exps + e0 * o.fr_bytes, cnt * o.fr_bytes, cudaMemcpyHostToDevice, s));
+                d_exps = be;
+            }
+            d_in = bi;
+            d_out = bo;
+        } else {
+            d_in = j.in + e0 * isz;
+            d_out = j.out + e0 * osz;
+            if (j.exps) d_exps = j.exps + e0 * o.fr_bytes;
+        }
+        DecodeArgs da;
+        da.in = reinterpret_cast<const uint32_t*>(d_in);
+        da.in_compressed = j.in_c;
+        da.check = j.check;
+        da.n = cnt;
+        da.aff = aff;
+        da.inf = inf;
+        da.status = d_status + t;
+        o.decode(da, s);
+        ScalarMulArgs a;
+        a.aff = aff;
+        a.inf = inf;
+        a.n = cnt;
+        a.exps = reinterpret_cast<const uint32_t*>(d_exps);
+        a.tau_tab = j.d_tab;
+        a.first_power = j.first_power + e0;
+        a.coeff_m = j.d_coeff_m;
+        a.has_coeff = j.has_coeff;
+        a.jac = jac;
+        o.scalar_mul(a, s);
+        NormalizeArgs na;
+        na.jac = jac;
+        na.n = cnt;
+        na.prefix = prefix;
+        na.out = reinterpret_cast<uint32_t*>(d_out);
+        na.out_compressed = j.out_c;
+        na.threads = normalize_threads(cnt);
+        o.normalize_encode(na, s);
+        if (host) CU(cudaMemcpyAsync(j.out + e0 * osz, d_out, cnt * osz, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaGetLastError());
+    for (int k = 0; k < nl; k++) CU(cudaStreamSynchronize((!host && user_stream) ? user_stream : lg[k].l->stream));
+    if (ev_init) cudaEventDestroy(ev_init);
+    CU(cudaMemcpy(st.data(), d_status, ntiles * 8, cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < ntiles && rc == SS_OK; t++) rc = decode_status(st[t], t * T, j.what);
+    return rc;
+}
+
+// scalar context: uploads tau / coefficients and builds the tau^(2^j) table on the device
+struct ScalarSetup {
+    uint8_t* slab = nullptr;
+    uint32_t* d_tab = nullptr;
+    uint32_t* d_coeff_m[3] = {nullptr, nullptr, nullptr};
+    ~ScalarSetup() {
+        if (slab) cudaFree(slab);
+    }
+    // coeffs[k] may be null -> Montgomery one
+    int init(const GroupOps& o, const uint8_t* tau, const uint8_t* const coeffs[3], cudaStream_t s) {
+        const size_t fb = o.fr_bytes, fw = o.fr_words;
+        const size_t tab_b = align_up(64 * fw * 4, 256), el_b = align_up(fw * 4, 256);
+        CU(cudaMalloc(&slab, tab_b + 3 * el_b + 4 * el_b));
+        d_tab = reinterpret_cast<uint32_t*>(slab);
+        uint8_t* p = slab + tab_b;
+        for (int k = 0; k < 3; k++) d_coeff_m[k] = reinterpret_cast<uint32_t*>(p + k * el_b);
+        uint8_t* raw = p + 3 * el_b;  // tau, c0, c1, c2 canonical
+        std::vector<uint8_t> zero(fb, 0);
+        CU(cudaMemcpyAsync(raw, tau ? tau : zero.data(), fb, cudaMemcpyHostToDevice, s));
+        for (int k = 0; k < 3; k++)
+            if (coeffs[k]) CU(cudaMemcpyAsync(raw + (k + 1) * el_b, coeffs[k], fb, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));  // `zero` goes out of scope
+        for (int k = 0; k < 3; k++)
+            o.prepare_scalars(reinterpret_cast<uint32_t*>(raw),
+                              coeffs[k] ? reinterpret_cast<uint32_t*>(raw + (k + 1) * el_b) : nullptr,
+                              d_tab, d_coeff_m[k], s);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        return SS_OK;
+    }
+};
+
+bool scalar_is_canonical(int curve, const uint8_t* s) {
+    // r for BLS12-377 (32 bytes) / BW6-761 (48 bytes), little-endian compare from the top
+    static const uint32_t r_bls[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
+    static const uint32_t r_bw6[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+    const uint32_t* r = curve == SS_CURVE_BLS12_377 ? r_bls : r_bw6;
+    int n = curve == SS_CURVE_BLS12_377 ? 8 : 12;
+    for (int i = n - 1; i >= 0; i--) {
+        uint32_t w;
+        memcpy(&w, s + 4 * i, 4);
+        if (w < r[i]) return true;
+        if (w > r[i]) return false;
+    }
+    return false;
+}
+
+int phase1_sizes(const ss_phase1_params* p, ss_phase1_sizes* o) {
+    if (!p || !o) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    const GroupOps* g1 = group_ops(p->curve, SS_G1);
+    const GroupOps* g2 = group_ops(p->curve, SS_G2);
+    if (!g1 || !g2) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve %d", p->curve);
+    if (p->total_size_in_log2 == 0 || p->total_size_in_log2 > 40)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad power %u", p->total_size_in_log2);
+    const uint64_t pl = 1ull << p->total_size_in_log2, pg1 = (pl << 1) - 1;
+    const uint64_t upper = p->proving_system == SS_GROTH16 ? pg1 : pl;
+    uint64_t start = 0, end = upper;
+    if (p->contribution_mode == SS_MODE_CHUNKED) {
+        start = p->chunk_index * p->chunk_size;
+        end = (p->chunk_index + 1) * p->chunk_size;
+        if (p->chunk_size == 0 || start >= upper) return fail(SS_ERR_INVALID_CHUNK, 0, 0, 0, "chunk out of range");
+    }
+    o->powers_length = pl;
+    o->powers_g1_length = pg1;
+    o->g1_chunk_size = end > upper ? upper - start : end - start;
+    if (p->proving_system == SS_GROTH16) {
+        if (end > pl && start >= pl) o->other_chunk_size = 0;
+        else if (end > pl) o->other_chunk_size = pl - start;
+        else o->other_chunk_size = end - start;
+    } else {
+        o->other_chunk_size = 0;
+    }
+    o->hash_size = 64;
+    o->public_key_size = 3 * (uint64_t)g2->csize + 6 * (uint64_t)g1->csize;
+    const uint64_t k = p->total_size_in_log2;
+    if (p->proving_system == SS_GROTH16) {
+        o->accumulator_size = o->g1_chunk_size * g1->usize + o->other_chunk_size * (g2->usize + 2 * (uint64_t)g1->usize) + g2->usize + 64;
+        o->contribution_size = o->g1_chunk_size * g1->csize + o->other_chunk_size * (g2->csize + 2 * (uint64_t)g1->csize) + g2->csize + 64 + o->public_key_size;
+    } else {
+        uint64_t xu = 0, xc = 0;
+        if (p->chunk_index == 0) {
+            xu = 3 * (uint64_t)g1->usize + 3 * k * g1->usize + (k + 2) * g2->usize;
+            xc = 3 * (uint64_t)g1->csize + 3 * k * g1->csize + (k + 2) * g2->csize;
+        }
+        o->accumulator_size = o->g1_chunk_size * g1->usize + xu + 64;
+        o->contribution_size = o->g1_chunk_size * g1->csize + xc + 64 + o->public_key_size;
+    }
+    return SS_OK;
+}
+
+int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
+                            size_t output_len, int cin, int cout, int check, const uint8_t* tau,
+                            const uint8_t* alpha, const uint8_t* beta, bool host, cudaStream_t user_stream) {
+    if (!p || !input || !output || !tau || !alpha || !beta) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (check < 0 || check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode %d", check);
+    if (p->proving_system != SS_GROTH16)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "only the Groth16 accumulator layout is implemented");
+    ss_phase1_sizes z;
+    int rc = phase1_sizes(p, &z);
+    if (rc) return rc;
+    const GroupOps& g1 = *group_ops(p->curve, SS_G1);
+    const GroupOps& g2 = *group_ops(p->curve, SS_G2);
+    const uint64_t need_in = cin ? z.contribution_size - z.public_key_size : z.accumulator_size;
+    const uint64_t need_out = cout ? z.contribution_size - z.public_key_size : z.accumulator_size;
+    if (input_len < need_in) return fail(SS_ERR_INVALID_LENGTH, 0, need_in, input_len, "input buffer too short");
+    if (output_len < need_out) return fail(SS_ERR_INVALID_LENGTH, 0, need_out, output_len, "output buffer too short");
+    for (const uint8_t* s : {tau, alpha, beta})
+        if (!scalar_is_canonical(p->curve, s)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "scalar >= r");
+    if ((rc = ensure_init())) return rc;
+    const int device = g_devices[0];
+    CU(cudaSetDevice(device));
+
+    LaneGuard setup_lane;
+    if ((rc = lane_acquire(device, 4096, &setup_lane.l))) return rc;
+    ScalarSetup sc;
+    const uint8_t* coeffs[3] = {nullptr, alpha, beta};
+    if ((rc = sc.init(g1, tau, coeffs, setup_lane.l->stream))) return rc;
+
+    // split (buffers.rs:293-341): [hash][tau_g1][tau_g2][alpha_g1][beta_g1][beta_g2]
+    auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
+    const uint64_t n1 = z.g1_chunk_size, n2 = z.other_chunk_size;
+    uint64_t oi[5], oo[5];
+    {
+        uint64_t a = 64, b = 64;
+        const uint64_t cnt[5] = {n1, n2, n2, n2, 1};
+        const GroupOps* gs[5] = {&g1, &g2, &g1, &g1, &g2};
+        for (int v = 0; v < 5; v++) {
+            oi[v] = a;
+            oo[v] = b;
+            a += cnt[v] * sz(*gs[v], cin);
+            b += cnt[v] * sz(*gs[v], cout);
+        }
+    }
+    const uint64_t first = p->contribution_mode == SS_MODE_CHUNKED ? p->chunk_index * p->chunk_size : 0;
+    VectorJob jobs[5] = {
+        // tau_g1 <- tau^i
+        {&g1, input + oi[0], output + oo[0], cin, cout, check, n1, nullptr, sc.d_tab, first, sc.d_coeff_m[0], 0, "tau_g1"},
+        // tau_g2 <- tau^i
+        {&g2, input + oi[1], output + oo[1], cin, cout, check, n2, nullptr, sc.d_tab, first, sc.d_coeff_m[0], 0, "tau_g2"},
+        // alpha_g1 <- alpha tau^i
+        {&g1, input + oi[2], output + oo[2], cin, cout, check, n2, nullptr, sc.d_tab, first, sc.d_coeff_m[1], 1, "alpha_g1"},
+        // beta_g1 <- beta tau^i
+        {&g1, input + oi[3], output + oo[3], cin, cout, check, n2, nullptr, sc.d_tab, first, sc.d_coeff_m[2], 1, "beta_g1"},
+        // beta_g2 <- beta   (computation.rs:42-50): tau^0 * beta
+        {&g2, input + oi[4], output + oo[4], cin, cout, check, 1, nullptr, sc.d_tab, 0, sc.d_coeff_m[2], 1, "beta_g2"},
+    };
+    for (int v = 0; v < 5; v++)
+        if ((rc = run_vector_on(device, jobs[v], host, user_stream))) return rc;
+    return SS_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* ss_version(void) { return "snark-setup-b200 0.1 (sm_100a)"; }
+
+void ss_last_error(ss_error_info* out) {
+    if (out) *out = g_err;
+}
+
+int ss_init(const int* devices, int n_devices) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_devices.clear();
+        for (int i = 0; i < n_devices; i++) g_devices.push_back(devices[i]);
+        g_inited = false;
+    }
+    return ensure_init();
+}
+
+void ss_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (Lane* l : g_lanes) {
+        cudaSetDevice(l->device);
+        if (l->buf) cudaFree(l->buf);
+        if (l->stream) cudaStreamDestroy(l->stream);
+        delete l;
+    }
+    g_lanes.clear();
+    g_inited = false;
+}
+
+int ss_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+size_t ss_element_size(int curve, int group, int compressed) {
+    const GroupOps* o = group_ops(curve, group);
+    if (!o) return 0;
+    return compressed ? o->csize : o->usize;
+}
+
+size_t ss_scalar_size(int curve) {
+    const GroupOps* o = group_ops(curve, SS_G1);
+    return o ? o->fr_bytes : 0;
+}
+
+int ss_generate_powers_of_tau(int curve, const uint8_t* tau, uint64_t start, uint64_t end, uint8_t* out) {
+    const GroupOps* o = group_ops(curve, SS_G1);
+    if (!o || !tau || (!out && end > start)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad argument");
+    if (end <= start) return SS_OK;
+    if (!scalar_is_canonical(curve, tau)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "tau >= r");
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int device = g_devices[0];
+    const uint64_t n = end - start;
+    LaneGuard lg;
+    if ((rc = lane_acquire(device, n * o->fr_bytes + 256, &lg.l))) return rc;
+    ScalarSetup sc;
+    const uint8_t* coeffs[3] = {nullptr, nullptr, nullptr};
+    if ((rc = sc.init(*o, tau, coeffs, lg.l->stream))) return rc;
+    o->powers(sc.d_tab, start, n, reinterpret_cast<uint32_t*>(lg.l->buf), lg.l->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, lg.l->buf, n * o->fr_bytes, cudaMemcpyDeviceToHost, lg.l->stream));
+    CU(cudaStreamSynchronize(lg.l->stream));
+    return SS_OK;
+}
+
+int ss_apply_powers(int curve, int group, const uint8_t* in, int in_compressed, int in_check, uint8_t* out,
+                    int out_compressed, size_t n, const uint8_t* powers, const uint8_t* tau, uint64_t first_power,
+                    const uint8_t* coeff) {
+    const GroupOps* o = group_ops(curve, group);
+    if (!o) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group %d/%d", curve, group);
+    if (n == 0) return SS_OK;
+    if (!in || !out || (!powers && !tau)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (in_check < 0 || in_check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode");
+    if (tau && !powers && !scalar_is_canonical(curve, tau)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "tau >= r");
+    if (coeff && !scalar_is_canonical(curve, coeff)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "coeff >= r");
+    if (powers)
+        for (size_t i = 0; i < n; i++)
+            if (!scalar_is_canonical(curve, powers + i * o->fr_bytes))
+                return fail(SS_ERR_INVALID_DATA, i, 0, 0, "scalar %zu >= r", i);
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int device = g_devices[0];
+    LaneGuard lg;
+    if ((rc = lane_acquire(device, 4096, &lg.l))) return rc;
+    ScalarSetup sc;
+    const uint8_t* coeffs[3] = {coeff, nullptr, nullptr};
+    if ((rc = sc.init(*o, powers ? nullptr : tau, coeffs, lg.l->stream))) return rc;
+    VectorJob j = {o, in, out, in_compressed, out_compressed, in_check, n, powers, sc.d_tab, first_power,
+                   sc.d_coeff_m[0], coeff ? 1 : 0, "apply_powers"};
+    return run_vector_on(device, j, true, nullptr);
+}
+
+int ss_batch_exp(int curve, int group, uint8_t* bases, size_t n, const uint8_t* exps, size_t n_exps,
+                 const uint8_t* coeff) {
+    if (n != n_exps) return fail(SS_ERR_INVALID_LENGTH, 0, n, n_exps, "bases.len() != exps.len()");
+    return ss_apply_powers(curve, group, bases, 0, SS_CHECK_NO, bases, 0, n, exps, nullptr, 0, coeff);
+}
+
+int ss_batch_mul(int curve, int group, uint8_t* bases, size_t n, const uint8_t* coeff) {
+    if (!coeff) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null coeff");
+    // every exponent equal to coeff == tau^0 * coeff
+    const GroupOps* o = group_ops(curve, group);
+    if (!o) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group");
+    std::vector<uint8_t> one(o->fr_bytes, 0);
+    one[0] = 1;
+    if (n == 0) return SS_OK;
+    if (!bases) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null bases");
+    if (!scalar_is_canonical(curve, coeff)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "coeff >= r");
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int device = g_devices[0];
+    LaneGuard lg;
+    if ((rc = lane_acquire(device, 4096, &lg.l))) return rc;
+    ScalarSetup sc;
+    const uint8_t* coeffs[3] = {coeff, nullptr, nullptr};
+    if ((rc = sc.init(*o, one.data(), coeffs, lg.l->stream))) return rc;
+    // first_power = 0 for every element: use a zero-stride trick by exponent 0 -> tau^0; the kernel
+    // adds the element index, so pass tau = 1 (1^i = 1).
+    VectorJob j = {o, bases, bases, 0, 0, SS_CHECK_NO, n, nullptr, sc.d_tab, 0, sc.d_coeff_m[0], 1, "batch_mul"};
+    return run_vector_on(device, j, true, nullptr);
+}
+
+// decode (+ optional subgroup r-mul) (+ optional re-encode) over host buffers, tile by tile
+static int transcode_impl(int curve, int group, const uint8_t* in, int in_compressed, int check, uint8_t* out,
+                          int out_compressed, size_t n, bool rmul_subgroup) {
+    const GroupOps* o = group_ops(curve, group);
+    if (!o) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group");
+    if (n == 0) return SS_OK;
+    if (!in) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null input");
+    if (check < 0 || check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode");
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int device = g_devices[0];
+    const size_t isz = in_compressed ? o->csize : o->usize, osz = out_compressed ? o->csize : o->usize;
+    const size_t T = std::min<size_t>(tile_elems(), n);
+    LaneGuard lg;
+    const size_t aff_b = align_up((size_t)2 * o->coord_words * 4 * T, 256);
+    if ((rc = lane_acquire(device, 256 + align_up(isz * T, 256) + align_up(osz * T, 256) + aff_b + align_up(T, 256), &lg.l)))
+        return rc;
+    cudaStream_t s = lg.l->stream;
+    Carver cv(lg.l->buf);
+    unsigned long long* d_status = cv.take<unsigned long long>(16);
+    uint8_t* bi = cv.take<uint8_t>(isz * T);
+    uint8_t* bo = cv.take<uint8_t>(osz * T);
+    uint32_t* aff = cv.take<uint32_t>((size_t)2 * o->coord_words * 4 * T);
+    uint8_t* inf = cv.take<uint8_t>(T);
+    for (size_t e0 = 0; e0 < n; e0 += T) {
+        const size_t cnt = std::min(T, n - e0);
+        CU(cudaMemsetAsync(d_status, 0xff, 16, s));
+        CU(cudaMemcpyAsync(bi, in + e0 * isz, cnt * isz, cudaMemcpyHostToDevice, s));
+        DecodeArgs da = {reinterpret_cast<const uint32_t*>(bi), in_compressed, check, cnt, aff, inf, d_status};
+        o->decode(da, s);
+        if (rmul_subgroup) {
+            SubgroupArgs sa = {aff, inf, cnt, d_status + 1};
+            o->subgroup(sa, s);
+        }
+        if (out) {
+            EncodeArgs ea = {aff, inf, cnt, reinterpret_cast<uint32_t*>(bo), out_compressed};
+            o->encode(ea, s);
+        }
+        CU(cudaGetLastError());
+        unsigned long long st[2];
+        CU(cudaMemcpyAsync(st, d_status, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if ((rc = decode_status(st[0], e0, "read_batch"))) return rc;
+        if ((rc = decode_status(st[1], e0, "check_subgroup"))) return rc;
+        if (out) {
+            CU(cudaMemcpyAsync(out + e0 * osz, bo, cnt * osz, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
+    }
+    return SS_OK;
+}
+
+int ss_transcode(int curve, int group, const uint8_t* in, int in_compressed, int check, uint8_t* out,
+                 int out_compressed, size_t n) {
+    return transcode_impl(curve, group, in, in_compressed, check, out, out_compressed, n, false);
+}
+
+int ss_check_subgroup(int curve, int group, const uint8_t* in, int compressed, size_t n, int subgroup_mode) {
+    if (subgroup_mode < 0 || subgroup_mode > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad subgroup mode");
+    // elements were read by the caller with Validate::No; every mode but `No` collapses to the direct
+    // r-multiplication (setup-utils/src/elements.rs:129-144)
+    return transcode_impl(curve, group, in, compressed, SS_CHECK_NO, nullptr, 0, n, subgroup_mode != SS_SUBGROUP_NO);
+}
+
+int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out) { return phase1_sizes(p, out); }
+
+int ss_phase1_computation(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
+                          size_t output_len, int compressed_input, int compressed_output, int check_input,
+                          const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta) {
+    return phase1_computation_impl(p, input, input_len, output, output_len, compressed_input, compressed_output,
+                                   check_input, tau, alpha, beta, true, nullptr);
+}
+
+int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, size_t input_len, void* d_output,
+                              size_t output_len, int compressed_input, int compressed_output, int check_input,
+                              const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, void* stream) {
+    return phase1_computation_impl(p, static_cast<const uint8_t*>(d_input), input_len, static_cast<uint8_t*>(d_output),
+                                   output_len, compressed_input, compressed_output, check_input, tau, alpha, beta,
+                                   false, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

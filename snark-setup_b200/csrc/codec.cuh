@@ -1,0 +1,160 @@
+// Canonical point (de)serialisation on the device.
+//
+// Byte format = ark-serialize 0.4 / ark-ec 0.4 short-Weierstrass:
+// little-endian canonical field elements, flags in the two top bits of the last byte
+// (0x80 = y is the lexicographically larger root, 0x40 = point at infinity); Fp2 = c0 || c1 with
+// the flags on c1; compressed = x+flags, uncompressed = x || y+flags.
+// Semantics of the validation modes follow `Deserializer::read_element`
+// (setup-utils/src/io/read.rs:57-73) and `CheckForCorrectness -> Validate`
+// (setup-utils/src/elements.rs:36-43); encoding follows `Serializer::write_element`
+// (setup-utils/src/io/write.rs:30-35).
+// All element sizes are multiples of 4 bytes, so elements are moved as little-endian u32 words,
+// which are the limbs themselves.
+#pragma once
+#include "ec.cuh"
+
+namespace ss {
+
+enum : int {
+    ERR_OK = 0,
+    ERR_INVALID_DATA = 1,       // SerializationError::InvalidData (non-canonical, non-square, failed Validate::Yes)
+    ERR_UNEXPECTED_FLAGS = 2,   // SerializationError::UnexpectedFlags (both flag bits set)
+    ERR_POINT_AT_INFINITY = 3,  // Error::PointAtInfinity
+    ERR_INCORRECT_SUBGROUP = 4  // Error::IncorrectSubgroup
+};
+enum : int { CHECK_FULL = 0, CHECK_ONLY_NON_ZERO = 1, CHECK_ONLY_IN_GROUP = 2, CHECK_NO = 3 };
+
+constexpr uint32_t FLAG_NEG_W = 0x80000000u;  // in the top word
+constexpr uint32_t FLAG_INF_W = 0x40000000u;
+
+template <class F>
+struct FieldIO;
+
+template <class P>
+struct FieldIO<Fp<P>> {
+    static constexpr int WORDS = P::N;
+    // raw words -> Montgomery element.  ERR_UNEXPECTED_FLAGS when both flag bits are set (checked
+    // first, as ark-ff deserialize_with_flags does), ERR_INVALID_DATA when the integer is >= p.
+    SS_HD static int load(const uint32_t* w, bool has_flags, Fp<P>& out, uint32_t& flags) {
+        Fp<P> raw;
+#pragma unroll
+        for (int i = 0; i < P::N; i++) raw.l[i] = w[i];
+        flags = 0;
+        if (has_flags) {
+            flags = raw.l[P::N - 1] & 0xc0000000u;
+            raw.l[P::N - 1] &= 0x3fffffffu;
+            if (flags == 0xc0000000u) return ERR_UNEXPECTED_FLAGS;
+        }
+        if (raw_ge_mod<P>(raw.l)) return ERR_INVALID_DATA;
+        out = fp_to_mont(raw);
+        return ERR_OK;
+    }
+    SS_HD static void store(uint32_t* w, const Fp<P>& canon, uint32_t flags) {
+#pragma unroll
+        for (int i = 0; i < P::N - 1; i++) w[i] = canon.l[i];
+        w[P::N - 1] = canon.l[P::N - 1] | flags;
+    }
+    SS_HD static Fp<P> canonical(const Fp<P>& m) { return fp_from_mont(m); }
+    // y > -y on canonical integers; `c` canonical
+    SS_HD static bool is_negative(const Fp<P>& c) {
+        if (c.is_zero()) return false;
+        uint32_t neg[P::N];
+        neg[0] = sub_cc(P::mod(0), c.l[0]);
+#pragma unroll
+        for (int i = 1; i < P::N - 1; i++) neg[i] = subc_cc(P::mod(i), c.l[i]);
+        neg[P::N - 1] = subc(P::mod(P::N - 1), c.l[P::N - 1]);
+        return raw_gt<P::N>(c.l, neg);
+    }
+};
+
+template <class P>
+struct FieldIO<Fp2<P>> {
+    using B = FieldIO<Fp<P>>;
+    static constexpr int WORDS = 2 * P::N;
+    SS_HD static int load(const uint32_t* w, bool has_flags, Fp2<P>& out, uint32_t& flags) {
+        uint32_t f0;
+        flags = 0;
+        int e = B::load(w, false, out.c0, f0);
+        if (e) return e;
+        return B::load(w + P::N, has_flags, out.c1, flags);
+    }
+    SS_HD static void store(uint32_t* w, const Fp2<P>& canon, uint32_t flags) {
+        B::store(w, canon.c0, 0);
+        B::store(w + P::N, canon.c1, flags);
+    }
+    SS_HD static Fp2<P> canonical(const Fp2<P>& m) { return Fp2<P>{fp_from_mont(m.c0), fp_from_mont(m.c1)}; }
+    // lexicographic, c1 first (ark-ff QuadExtField Ord)
+    SS_HD static bool is_negative(const Fp2<P>& c) {
+        if (!c.c1.is_zero()) return B::is_negative(c.c1);
+        return B::is_negative(c.c0);
+    }
+};
+
+// r * P == O  (the reference's explicit subgroup test, setup-utils/src/elements.rs:138-142)
+template <class G>
+SS_HD bool in_subgroup_rmul(const Affine<typename G::F>& p) {
+    using F = typename G::F;
+    Jac<F> t = jac_mul_bits<F>(p, [](int i) { return G::GP::order(i); }, G::GP::ORDER_BITS);
+    return t.is_identity();
+}
+
+// Decode one element.  Returns ERR_*; `out` is valid when ERR_OK.
+template <class G>
+SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typename G::F>& out) {
+    using F = typename G::F;
+    using IO = FieldIO<F>;
+    uint32_t flags;
+    out.inf = false;
+    int e;
+    if (compressed) {
+        if ((e = IO::load(w, true, out.x, flags)) != ERR_OK) return e;
+        if (flags & FLAG_INF_W) {
+            out.inf = true;
+        } else {
+            F rhs = fp_add(fp_mul(fp_sqr(out.x), out.x), G::b());
+            F y;
+            if (!fp_sqrt(rhs, y)) return ERR_INVALID_DATA;
+            bool neg = IO::is_negative(IO::canonical(y));
+            bool want_neg = (flags & FLAG_NEG_W) != 0;
+            out.y = (neg == want_neg) ? y : fp_neg(y);
+        }
+    } else {
+        uint32_t fx;
+        if ((e = IO::load(w, false, out.x, fx)) != ERR_OK) return e;
+        if ((e = IO::load(w + IO::WORDS, true, out.y, flags)) != ERR_OK) return e;
+        if (flags & FLAG_INF_W) out.inf = true;
+    }
+    if (out.inf) {
+        out.x = F::zero();
+        out.y = F::zero();
+    } else if (check == CHECK_FULL || check == CHECK_ONLY_IN_GROUP) {
+        if (!on_curve(out, G::b())) return ERR_INVALID_DATA;
+        if (!in_subgroup_rmul<G>(out)) return ERR_INVALID_DATA;
+    }
+    if ((check == CHECK_FULL || check == CHECK_ONLY_NON_ZERO) && out.inf) return ERR_POINT_AT_INFINITY;
+    return ERR_OK;
+}
+
+// Encode one affine element (Montgomery coordinates) to `w`.
+template <class G>
+SS_HD void encode_point(uint32_t* w, bool compressed, const Affine<typename G::F>& p) {
+    using F = typename G::F;
+    using IO = FieldIO<F>;
+    if (p.inf) {
+        const int words = compressed ? IO::WORDS : 2 * IO::WORDS;
+        for (int i = 0; i < words - 1; i++) w[i] = 0;
+        w[words - 1] = FLAG_INF_W;
+        return;
+    }
+    F xc = IO::canonical(p.x);
+    F yc = IO::canonical(p.y);
+    uint32_t flags = IO::is_negative(yc) ? FLAG_NEG_W : 0u;
+    if (compressed) {
+        IO::store(w, xc, flags);
+    } else {
+        IO::store(w, xc, 0);
+        IO::store(w + IO::WORDS, yc, flags);
+    }
+}
+
+}  // namespace ss

@@ -1,0 +1,216 @@
+// Short-Weierstrass (a = 0) group arithmetic in Jacobian coordinates, generic over the
+// coordinate field (Fp for BLS12-377 G1 and both BW6-761 groups, Fp2 for BLS12-377 G2).
+//
+// Device-side replacement for ark-ec 0.4 `short_weierstrass::{Affine, Projective}`:
+// `AffineRepr::mul` / `mul_bigint` (setup-utils/src/helpers.rs:64,104; elements.rs:138,142;
+// phase1/src/helpers/accumulator.rs:121,131).  Results are exact group elements, so any correct
+// formula set yields the bytes the reference produces once normalised and canonically encoded
+// (SURVEY.md Appendix A.3).
+#pragma once
+#include "constants_gen.cuh"
+#include "fp2.cuh"
+
+namespace ss {
+
+template <class F>
+struct Affine {
+    F x, y;
+    bool inf;
+};
+
+template <class F>
+struct Jac {
+    F X, Y, Z;  // Z == 0 <=> identity
+    SS_HD static Jac identity() { return Jac{F::one(), F::one(), F::zero()}; }
+    SS_HD bool is_identity() const { return Z.is_zero(); }
+};
+
+// ---- group descriptors -----------------------------------------------------------------------
+struct Bls377G1 {
+    using F = Fp<Bls377Fq>;
+    using Fr = Fp<Bls377Fr>;
+    using GP = Bls377G1Params;
+    static constexpr int COORD_LIMBS = 12;
+    static constexpr int USIZE = 96, CSIZE = 48;
+    SS_HD static F b() {
+        F r;
+#pragma unroll
+        for (int i = 0; i < 12; i++) r.l[i] = GP::b(i);
+        return r;
+    }
+    SS_HD static Affine<F> generator() {
+        Affine<F> g;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            g.x.l[i] = GP::gx(i);
+            g.y.l[i] = GP::gy(i);
+        }
+        g.inf = false;
+        return g;
+    }
+};
+
+struct Bls377G2 {
+    using F = Fp2<Bls377Fq>;
+    using Fr = Fp<Bls377Fr>;
+    using GP = Bls377G2Params;
+    static constexpr int USIZE = 192, CSIZE = 96;
+    SS_HD static F b() {
+        F r;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            r.c0.l[i] = GP::b_c0(i);
+            r.c1.l[i] = GP::b_c1(i);
+        }
+        return r;
+    }
+    SS_HD static Affine<F> generator() {
+        Affine<F> g;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            g.x.c0.l[i] = GP::gx_c0(i);
+            g.x.c1.l[i] = GP::gx_c1(i);
+            g.y.c0.l[i] = GP::gy_c0(i);
+            g.y.c1.l[i] = GP::gy_c1(i);
+        }
+        g.inf = false;
+        return g;
+    }
+};
+
+template <class GPx>
+struct Bw6Group {
+    using F = Fp<Bw6Fq>;
+    using Fr = Fp<Bls377Fq>;  // BW6-761's scalar field is BLS12-377's base field
+    using GP = GPx;
+    static constexpr int USIZE = 192, CSIZE = 96;
+    SS_HD static F b() {
+        F r;
+#pragma unroll
+        for (int i = 0; i < 24; i++) r.l[i] = GP::b(i);
+        return r;
+    }
+    SS_HD static Affine<F> generator() {
+        Affine<F> g;
+#pragma unroll
+        for (int i = 0; i < 24; i++) {
+            g.x.l[i] = GP::gx(i);
+            g.y.l[i] = GP::gy(i);
+        }
+        g.inf = false;
+        return g;
+    }
+};
+using Bw6G1 = Bw6Group<Bw6G1Params>;
+using Bw6G2 = Bw6Group<Bw6G2Params>;
+
+// ---- formulas ---------------------------------------------------------------------------------
+// dbl-2009-l (a = 0): 2M + 5S
+template <class F>
+SS_HD Jac<F> jac_dbl(const Jac<F>& p) {
+    if (p.Z.is_zero()) return p;
+    F A = fp_sqr(p.X);
+    F B = fp_sqr(p.Y);
+    F C = fp_sqr(B);
+    F t = fp_sqr(fp_add(p.X, B));
+    F D = fp_dbl(fp_sub(fp_sub(t, A), C));
+    F E = fp_add(fp_dbl(A), A);
+    F Fq = fp_sqr(E);
+    Jac<F> r;
+    r.X = fp_sub(Fq, fp_dbl(D));
+    F C8 = fp_dbl(fp_dbl(fp_dbl(C)));
+    r.Z = fp_dbl(fp_mul(p.Y, p.Z));
+    r.Y = fp_sub(fp_mul(E, fp_sub(D, r.X)), C8);
+    return r;
+}
+
+// madd-2007-bl: Jacobian + affine, 7M + 4S, with the exceptional cases handled
+template <class F>
+SS_HD Jac<F> jac_madd(const Jac<F>& p, const Affine<F>& q) {
+    if (q.inf) return p;
+    if (p.Z.is_zero()) return Jac<F>{q.x, q.y, F::one()};
+    F Z1Z1 = fp_sqr(p.Z);
+    F U2 = fp_mul(q.x, Z1Z1);
+    F S2 = fp_mul(fp_mul(q.y, p.Z), Z1Z1);
+    F H = fp_sub(U2, p.X);
+    F rr = fp_sub(S2, p.Y);
+    if (H.is_zero()) {
+        if (rr.is_zero()) return jac_dbl(p);
+        return Jac<F>::identity();
+    }
+    rr = fp_dbl(rr);
+    F HH = fp_sqr(H);
+    F I = fp_dbl(fp_dbl(HH));
+    F J = fp_mul(H, I);
+    F V = fp_mul(p.X, I);
+    Jac<F> r;
+    r.X = fp_sub(fp_sub(fp_sqr(rr), J), fp_dbl(V));
+    r.Y = fp_sub(fp_mul(rr, fp_sub(V, r.X)), fp_dbl(fp_mul(p.Y, J)));
+    r.Z = fp_sub(fp_sub(fp_sqr(fp_add(p.Z, H)), Z1Z1), HH);
+    return r;
+}
+
+// add-2007-bl: Jacobian + Jacobian, 11M + 5S
+template <class F>
+SS_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
+    if (p.Z.is_zero()) return q;
+    if (q.Z.is_zero()) return p;
+    F Z1Z1 = fp_sqr(p.Z);
+    F Z2Z2 = fp_sqr(q.Z);
+    F U1 = fp_mul(p.X, Z2Z2);
+    F U2 = fp_mul(q.X, Z1Z1);
+    F S1 = fp_mul(fp_mul(p.Y, q.Z), Z2Z2);
+    F S2 = fp_mul(fp_mul(q.Y, p.Z), Z1Z1);
+    F H = fp_sub(U2, U1);
+    F rr = fp_sub(S2, S1);
+    if (H.is_zero()) {
+        if (rr.is_zero()) return jac_dbl(p);
+        return Jac<F>::identity();
+    }
+    rr = fp_dbl(rr);
+    F I = fp_sqr(fp_dbl(H));
+    F J = fp_mul(H, I);
+    F V = fp_mul(U1, I);
+    Jac<F> r;
+    r.X = fp_sub(fp_sub(fp_sqr(rr), J), fp_dbl(V));
+    r.Y = fp_sub(fp_mul(rr, fp_sub(V, r.X)), fp_dbl(fp_mul(S1, J)));
+    r.Z = fp_mul(fp_sub(fp_sub(fp_sqr(fp_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
+    return r;
+}
+
+template <class F>
+SS_HD Affine<F> affine_neg(const Affine<F>& p) {
+    return Affine<F>{p.x, fp_neg(p.y), p.inf};
+}
+
+template <class F>
+SS_HD bool on_curve(const Affine<F>& p, const F& b) {
+    if (p.inf) return true;
+    return fp_sqr(p.y) == fp_add(fp_mul(fp_sqr(p.x), p.x), b);
+}
+
+// MSB-first double-and-add over `nbits` bits of a little-endian limb array (the reference
+// algorithm, kept as the simple/validated baseline and for the r-multiplication subgroup check).
+template <class F, class LimbFn>
+SS_HD Jac<F> jac_mul_bits(const Affine<F>& base, LimbFn limb, int nbits) {
+    Jac<F> acc = Jac<F>::identity();
+    if (base.inf) return acc;
+    for (int i = nbits - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((limb(i >> 5) >> (i & 31)) & 1) acc = jac_madd(acc, base);
+    }
+    return acc;
+}
+
+// Jacobian -> affine given 1/Z
+template <class F>
+SS_HD Affine<F> jac_to_affine_with_zinv(const Jac<F>& p, const F& zinv) {
+    F zi2 = fp_sqr(zinv);
+    Affine<F> r;
+    r.x = fp_mul(p.X, zi2);
+    r.y = fp_mul(p.Y, fp_mul(zi2, zinv));
+    r.inf = false;
+    return r;
+}
+
+}  // namespace ss

@@ -1,0 +1,318 @@
+// Montgomery prime-field arithmetic on N 32-bit limbs held in registers (N even).
+//
+// Replaces, on the device, what the reference gets from ark-ff 0.4 `Fp<MontBackend<_, N>>`
+// (call sites: setup-utils/src/helpers.rs:36,101,104; setup-utils/src/io/read.rs:63).
+//
+// Multiplication is operand scanning with interleaved reduction, written so that every
+// 32x32->64 product lands on an aligned (even, odd) register pair: the accumulator is kept as two
+// arrays, X holding the tiles at limb positions (0,1),(2,3).. and Y the tiles at (1,2),(3,4)..,
+// i.e. value = X + Y * 2^32.  Each tile update is `mad.lo.cc` + `madc.hi.cc` on one pair, which
+// ptxas turns into one IMAD.WIDE.U32.X; the carry runs along the whole array in one chain.  The
+// per-iteration division by 2^32 is free: X and Y swap roles (see mont_step).
+// Cost per multiplication: 2*N*N wide multiply-adds (N=12: 288) + N/2... see DESIGN.md.
+#pragma once
+#include "ptx.cuh"
+
+namespace ss {
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    using Params = P;
+    uint32_t l[N];
+
+    SS_HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    SS_HD static Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    SS_HD bool is_zero() const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= l[i];
+        return t == 0;
+    }
+    SS_HD bool operator==(const Fp& o) const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= l[i] ^ o.l[i];
+        return t == 0;
+    }
+    SS_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+};
+
+// r = (a >= p) ? a - p : a      (a < 2p)
+template <class P>
+SS_HD void fp_final_sub(uint32_t* a) {
+    constexpr int N = P::N;
+    uint32_t t[N];
+    t[0] = sub_cc(a[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(a[i], P::mod(i));
+    uint32_t borrow = subc(0, 0);  // 0xffffffff when a < p
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = borrow ? a[i] : t[i];
+}
+
+template <class P>
+SS_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);  // p has spare top bits: no carry out
+    fp_final_sub<P>(r.l);
+    return r;
+}
+
+template <class P>
+SS_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = subc(0, 0);
+    // add back p under mask
+    r.l[0] = add_cc(r.l[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & borrow);
+    r.l[N - 1] = addc(r.l[N - 1], P::mod(N - 1) & borrow);
+    return r;
+}
+
+template <class P>
+SS_HD Fp<P> fp_neg(const Fp<P>& a) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    uint32_t nz = a.is_zero() ? 0u : 0xffffffffu;
+    r.l[0] = sub_cc(P::mod(0), a.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(P::mod(i), a.l[i]);
+    r.l[N - 1] = subc(P::mod(N - 1), a.l[N - 1]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] &= nz;
+    return r;
+}
+
+template <class P>
+SS_HD Fp<P> fp_dbl(const Fp<P>& a) {
+    return fp_add(a, a);
+}
+
+// ---- Montgomery multiplication -------------------------------------------------------------
+// X[k] sits at limb position k, Y[k] at position k+1.
+// reduce: m = X[0]*INV ; (X,Y) += m*p  => X[0] == 0
+template <class P>
+SS_HD void mont_reduce_step(uint32_t* X, uint32_t* Y) {
+    constexpr int N = P::N;
+    uint32_t m = mul_lo(X[0], P::inv());
+    // odd limbs of p into Y
+    Y[0] = mad_lo_cc(P::mod(1), m, Y[0]);
+    Y[1] = madc_hi_cc(P::mod(1), m, Y[1]);
+#pragma unroll
+    for (int j = 2; j < N - 2; j += 2) {
+        Y[j] = madc_lo_cc(P::mod(j + 1), m, Y[j]);
+        Y[j + 1] = madc_hi_cc(P::mod(j + 1), m, Y[j + 1]);
+    }
+    Y[N - 2] = madc_lo_cc(P::mod(N - 1), m, Y[N - 2]);
+    Y[N - 1] = madc_hi(P::mod(N - 1), m, Y[N - 1]);
+    // even limbs of p into X
+    X[0] = mad_lo_cc(P::mod(0), m, X[0]);
+    X[1] = madc_hi_cc(P::mod(0), m, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(P::mod(j), m, X[j]);
+        X[j + 1] = madc_hi_cc(P::mod(j), m, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0);
+}
+
+// One operand-scanning step for bi, entered with the previous step's X (now E, aligned k-1 after
+// the implicit >>32, E[0] == 0) and Y (now aligned k).  On exit roles are (X=oldY, Y=oldX).
+template <class P>
+SS_HD void mont_step(uint32_t* X /*old Y*/, uint32_t* Y /*old X*/, const uint32_t* a, uint32_t bi) {
+    constexpr int N = P::N;
+    X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        Y[j] = madc_lo_cc(a[j + 1], bi, Y[j + 2]);
+        Y[j + 1] = madc_hi_cc(a[j + 1], bi, Y[j + 3]);
+    }
+    Y[N - 2] = madc_lo_cc(a[N - 1], bi, 0);
+    Y[N - 1] = madc_hi(a[N - 1], bi, 0);
+    X[0] = mad_lo_cc(a[0], bi, X[0]);
+    X[1] = madc_hi_cc(a[0], bi, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(a[j], bi, X[j]);
+        X[j + 1] = madc_hi_cc(a[j], bi, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0);
+    mont_reduce_step<P>(X, Y);
+}
+
+template <class P>
+SS_HD Fp<P> fp_mul_inl(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t X[N], Y[N];
+    // first step: plain products
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        X[j] = mul_lo(a.l[j], b.l[0]);
+        X[j + 1] = mul_hi(a.l[j], b.l[0]);
+        Y[j] = mul_lo(a.l[j + 1], b.l[0]);
+        Y[j + 1] = mul_hi(a.l[j + 1], b.l[0]);
+    }
+    mont_reduce_step<P>(X, Y);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_step<P>(Y, X, a.l, b.l[i]);
+        if (i + 1 < N) mont_step<P>(X, Y, a.l, b.l[i + 1]);
+    }
+    // after an odd number of role swaps: X-role = Y, Y-role = X.  result = Yrole + (Xrole >> 32)
+    Fp<P> r;
+    r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(X[j], Y[j + 1]);
+    r.l[N - 1] = addc(X[N - 1], 0);
+    fp_final_sub<P>(r.l);
+    return r;
+}
+
+// By default the multiplier is ONE out-of-line function per field and kernel: operands travel in
+// registers (no local memory), the call costs ~50 MOVs that issue in the shadow of the IMAD pipe,
+// and kernels stay a few thousand instructions long instead of hundreds of KB of inlined
+// carry chains.  -DSS_MUL_INLINE restores full inlining (for A/B measurements).
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) {
+    return fp_mul_inl(a, b);
+}
+#endif
+
+template <class P>
+SS_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+    return fp_mul_call<P>(a, b);
+#else
+    return fp_mul_inl(a, b);
+#endif
+}
+
+template <class P>
+SS_HD Fp<P> fp_sqr(const Fp<P>& a) {
+    return fp_mul(a, a);
+}
+
+// Montgomery form <-> canonical integer
+template <class P>
+SS_HD Fp<P> fp_to_mont(const Fp<P>& a) {
+    Fp<P> r2;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r2.l[i] = P::r2(i);
+    return fp_mul(a, r2);
+}
+
+template <class P>
+SS_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+    Fp<P> o = Fp<P>::zero();
+    o.l[0] = 1;
+    return fp_mul(a, o);
+}
+
+// a^e, e given as a limb accessor (runtime-indexed constant table), MSB first
+template <class P, class E>
+SS_HD Fp<P> fp_pow(const Fp<P>& a, E exp_limb, int nlimbs) {
+    Fp<P> r = Fp<P>::one();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--) {
+        uint32_t w = exp_limb(i);
+        for (int b = 31; b >= 0; b--) {
+            if (started) r = fp_sqr(r);
+            if ((w >> b) & 1) {
+                r = started ? fp_mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+
+template <class P>
+SS_HD Fp<P> fp_inv(const Fp<P>& a) {  // Fermat; 0 -> 0
+    return fp_pow<P>(a, [](int i) { return P::pm2(i); }, P::N);
+}
+
+// canonical-integer comparison of two RAW (non-Montgomery) limb arrays: a > b
+template <int N>
+SS_HD bool raw_gt(const uint32_t* a, const uint32_t* b) {
+    // b - a borrows  <=>  a > b
+    uint32_t t = sub_cc(b[0], a[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) t = subc_cc(b[i], a[i]);
+    (void)t;
+    return subc(0, 0) != 0;
+}
+
+template <class P>
+SS_HD bool raw_ge_mod(const uint32_t* a) {  // a >= p
+    uint32_t t = sub_cc(a[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < P::N; i++) t = subc_cc(a[i], P::mod(i));
+    (void)t;
+    return subc(0, 0) == 0;
+}
+
+// Square root.  Returns false when a is a non-residue.  Any root is acceptable: callers order
+// (y, -y) canonically afterwards (ark-ec get_ys_from_x_unchecked).
+template <class P>
+SS_HD bool fp_sqrt(const Fp<P>& a, Fp<P>& out) {
+    if (a.is_zero()) {
+        out = a;
+        return true;
+    }
+    if (P::P3MOD4) {
+        Fp<P> r = fp_pow<P>(a, [](int i) { return P::pp1q(i); }, P::N);
+        out = r;
+        return fp_sqr(r) == a;
+    } else {
+        // Tonelli-Shanks, p - 1 = 2^s * t
+        Fp<P> w = fp_pow<P>(a, [](int i) { return P::tm1h(i); }, P::N);  // a^((t-1)/2)
+        Fp<P> x = fp_mul(a, w);                                           // a^((t+1)/2)
+        Fp<P> b = fp_mul(x, w);                                           // a^t
+        Fp<P> z;
+#pragma unroll
+        for (int i = 0; i < P::N; i++) z.l[i] = P::root_of_unity(i);
+        const Fp<P> one = Fp<P>::one();
+        int v = P::TWO_ADICITY;
+        while (!(b == one)) {
+            int k = 0;
+            Fp<P> b2k = b;
+            while (!(b2k == one)) {
+                b2k = fp_sqr(b2k);
+                k++;
+                if (k == v) return false;  // non-residue
+            }
+            Fp<P> wj = z;
+            for (int j = 0; j < v - k - 1; j++) wj = fp_sqr(wj);
+            z = fp_sqr(wj);
+            b = fp_mul(b, z);
+            x = fp_mul(x, wj);
+            v = k;
+        }
+        out = x;
+        return true;
+    }
+}
+
+}  // namespace ss

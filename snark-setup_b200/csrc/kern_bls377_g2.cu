@@ -1,0 +1,9 @@
+// Kernel instantiations for Bls377G2 (one translation unit per group keeps nvcc compile times parallel).
+#include "kernels.cuh"
+
+namespace ss {
+const GroupOps& ops_bls377_g2() {
+    static const GroupOps o = GroupLaunch<Bls377G2>::ops();
+    return o;
+}
+}  // namespace ss

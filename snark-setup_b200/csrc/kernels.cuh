@@ -1,0 +1,361 @@
+// Device kernels of the batch-exponentiation path, generic over the group descriptor G
+// (Bls377G1, Bls377G2, Bw6G1, Bw6G2).  One translation unit per group instantiates them
+// (kern_*.cu) and publishes a GroupOps table; api.cu only sees that table.
+//
+// Data layout in HBM
+//   * serialized elements: exactly the reference's byte layout (packed, no header), read/written
+//     as u32 words — every element size is a multiple of 16 bytes.
+//   * Jacobian scratch `jac`: limb-major SoA, word (c*FW + w) of element i at jac[(c*FW+w)*n + i]
+//     (c = X,Y,Z; FW = words per coordinate) so that every warp access is one coalesced 128-byte
+//     line.
+//   * `prefix`: FW words per element, same limb-major layout, holds the running Z products of the
+//     Montgomery batch inversion.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "codec.cuh"
+
+namespace ss {
+
+// lowest failing index wins: status = min over failures of (index << 8 | code)
+constexpr unsigned long long STATUS_OK = ~0ull;
+
+SS_D void report(unsigned long long* status, uint64_t index, int code) {
+    atomicMin(status, (unsigned long long)((index << 8) | (uint64_t)code));
+}
+
+template <class F>
+struct FieldWords;
+template <class P>
+struct FieldWords<Fp<P>> {
+    static constexpr int W = P::N;
+    SS_D static void store(uint32_t* base, uint64_t stride, const Fp<P>& a) {
+#pragma unroll
+        for (int i = 0; i < P::N; i++) base[i * stride] = a.l[i];
+    }
+    SS_D static Fp<P> load(const uint32_t* base, uint64_t stride) {
+        Fp<P> a;
+#pragma unroll
+        for (int i = 0; i < P::N; i++) a.l[i] = base[i * stride];
+        return a;
+    }
+};
+template <class P>
+struct FieldWords<Fp2<P>> {
+    static constexpr int W = 2 * P::N;
+    SS_D static void store(uint32_t* base, uint64_t stride, const Fp2<P>& a) {
+        FieldWords<Fp<P>>::store(base, stride, a.c0);
+        FieldWords<Fp<P>>::store(base + P::N * stride, stride, a.c1);
+    }
+    SS_D static Fp2<P> load(const uint32_t* base, uint64_t stride) {
+        Fp2<P> a;
+        a.c0 = FieldWords<Fp<P>>::load(base, stride);
+        a.c1 = FieldWords<Fp<P>>::load(base + P::N * stride, stride);
+        return a;
+    }
+};
+
+// ---- scalar preparation -------------------------------------------------------------------------
+// tab[j] = tau^(2^j) (Montgomery), j < 64; coeff_m = coeff (Montgomery) or 1.
+template <class FrP>
+__global__ void k_prepare_scalars(const uint32_t* tau_le, const uint32_t* coeff_le, uint32_t* tab, uint32_t* coeff_m) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    constexpr int N = FrP::N;
+    Fp<FrP> t;
+    for (int i = 0; i < N; i++) t.l[i] = tau_le[i];
+    t = fp_to_mont(t);
+    for (int j = 0; j < 64; j++) {
+        for (int i = 0; i < N; i++) tab[j * N + i] = t.l[i];
+        t = fp_sqr(t);
+    }
+    Fp<FrP> c = Fp<FrP>::one();
+    if (coeff_le) {
+        for (int i = 0; i < N; i++) c.l[i] = coeff_le[i];
+        c = fp_to_mont(c);
+    }
+    for (int i = 0; i < N; i++) coeff_m[i] = c.l[i];
+}
+
+// tau^e from the table of tau^(2^j)   (== tau.pow([e]), setup-utils/src/helpers.rs:36)
+template <class FrP>
+SS_D Fp<FrP> tau_power(const uint32_t* __restrict__ tab, uint64_t e) {
+    constexpr int N = FrP::N;
+    Fp<FrP> r = Fp<FrP>::one();
+    bool started = false;
+    for (int j = 0; j < 64; j++) {
+        if ((e >> j) & 1) {
+            Fp<FrP> t;
+#pragma unroll
+            for (int i = 0; i < N; i++) t.l[i] = __ldg(tab + j * N + i);
+            r = started ? fp_mul(r, t) : t;
+            started = true;
+        }
+        if ((e >> j) <= 1) break;
+    }
+    return r;
+}
+
+// generate_powers_of_tau (setup-utils/src/helpers.rs:32-37): out[i] = canonical LE of tau^(start+i)
+template <class FrP>
+__global__ void k_powers(const uint32_t* __restrict__ tab, uint64_t start, uint64_t n, uint32_t* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<FrP> c = fp_from_mont(tau_power<FrP>(tab, start + i));
+#pragma unroll
+    for (int k = 0; k < FrP::N; k++) out[i * FrP::N + k] = c.l[k];
+}
+
+// ---- stage 1: read_batch ------------------------------------------------------------------------
+// Affine scratch `aff`: limb-major SoA [2*FW][n] (x then y, Montgomery) + one flag byte per element
+// (1 = point at infinity).
+struct DecodeArgs {
+    const uint32_t* in;  // serialized elements
+    int in_compressed;
+    int check;  // CHECK_*
+    uint64_t n;
+    uint32_t* aff;
+    uint8_t* inf;
+    unsigned long long* status;
+};
+
+// BatchDeserializer::read_batch (setup-utils/src/io/read.rs:110-135): one element per thread.
+template <class G>
+__global__ void __launch_bounds__(128) k_decode(DecodeArgs a) {
+    using F = typename G::F;
+    using FW = FieldWords<F>;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int ewords = (a.in_compressed ? G::CSIZE : G::USIZE) / 4;
+    Affine<F> p;
+    int e = decode_point<G>(a.in + i * ewords, a.in_compressed != 0, a.check, p);
+    if (e != ERR_OK) {
+        report(a.status, i, e);
+        p.inf = true;
+        p.x = F::zero();
+        p.y = F::zero();
+    }
+    FW::store(a.aff + i, a.n, p.x);
+    FW::store(a.aff + (uint64_t)FW::W * a.n + i, a.n, p.y);
+    a.inf[i] = p.inf ? 1 : 0;
+}
+
+template <class G>
+SS_D Affine<typename G::F> load_affine(const uint32_t* aff, const uint8_t* inf, uint64_t n, uint64_t i) {
+    using F = typename G::F;
+    using FW = FieldWords<F>;
+    Affine<F> p;
+    p.x = FW::load(aff + i, n);
+    p.y = FW::load(aff + (uint64_t)FW::W * n + i, n);
+    p.inf = inf[i] != 0;
+    return p;
+}
+
+// ---- stage 2: batch_exp core --------------------------------------------------------------------
+struct ScalarMulArgs {
+    const uint32_t* aff;  // decoded bases
+    const uint8_t* inf;
+    uint64_t n;
+    const uint32_t* exps;     // explicit canonical LE scalars [n][FRW], or nullptr
+    const uint32_t* tau_tab;  // [64][FRW] Montgomery, used when exps == nullptr
+    uint64_t first_power;     // exponent of element 0
+    const uint32_t* coeff_m;  // Montgomery coefficient (never null; 1 when absent)
+    int has_coeff;
+    uint32_t* jac;  // out: Jacobian, limb-major SoA [3*FW][n]
+};
+
+// bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
+// Jacobian form for k_normalize_encode.  v1: the reference's MSB-first double-and-add.
+template <class G>
+__global__ void __launch_bounds__(128) k_scalar_mul(ScalarMulArgs a) {
+    using F = typename G::F;
+    using FrP = typename G::Fr::Params;
+    using FW = FieldWords<F>;
+    constexpr int FRW = FrP::N;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Affine<F> base = load_affine<G>(a.aff, a.inf, a.n, i);
+    Fp<FrP> s;
+    if (a.exps) {
+#pragma unroll
+        for (int k = 0; k < FRW; k++) s.l[k] = a.exps[i * FRW + k];
+        if (a.has_coeff) {
+            Fp<FrP> c;
+#pragma unroll
+            for (int k = 0; k < FRW; k++) c.l[k] = __ldg(a.coeff_m + k);
+            s = fp_mul(s, c);  // canonical * Montgomery -> canonical
+        }
+    } else {
+        s = tau_power<FrP>(a.tau_tab, a.first_power + i);
+        if (a.has_coeff) {
+            Fp<FrP> c;
+#pragma unroll
+            for (int k = 0; k < FRW; k++) c.l[k] = __ldg(a.coeff_m + k);
+            s = fp_mul(s, c);
+        }
+        s = fp_from_mont(s);
+    }
+    Jac<F> r = jac_mul_bits<F>(base, [&](int k) { return s.l[k]; }, FrP::BITS);
+    uint32_t* o = a.jac + i;
+    FW::store(o, a.n, r.X);
+    FW::store(o + (uint64_t)FW::W * a.n, a.n, r.Y);
+    FW::store(o + (uint64_t)2 * FW::W * a.n, a.n, r.Z);
+}
+
+// ---- stage 3: normalize_batch + write_batch -----------------------------------------------------
+struct NormalizeArgs {
+    const uint32_t* jac;  // [3*FW][n]
+    uint64_t n;
+    uint32_t* prefix;  // scratch [FW][n]
+    uint32_t* out;     // serialized
+    int out_compressed;
+    uint32_t threads;  // T: thread t owns elements t, t+T, t+2T, ...
+};
+
+// CurveGroup::normalize_batch (Montgomery's trick, identities skipped) fused with
+// BatchSerializer::write_batch (setup-utils/src/helpers.rs:113-114, io/write.rs:57-66).
+template <class G>
+__global__ void __launch_bounds__(128) k_normalize_encode(NormalizeArgs a) {
+    using F = typename G::F;
+    using FW = FieldWords<F>;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.threads || t >= a.n) return;
+    const uint64_t n = a.n, T = a.threads;
+    const uint32_t* Zb = a.jac + (uint64_t)2 * FW::W * n;
+    F acc = F::one();
+    uint64_t last = t;
+    for (uint64_t e = t; e < n; e += T) {
+        F z = FW::load(Zb + e, n);
+        if (!z.is_zero()) {
+            FW::store(a.prefix + e, n, acc);
+            acc = fp_mul(acc, z);
+        }
+        last = e;
+    }
+    F inv = fp_inv(acc);
+    const int owords = (a.out_compressed ? G::CSIZE : G::USIZE) / 4;
+    for (uint64_t e = last;; e -= T) {
+        F z = FW::load(Zb + e, n);
+        Affine<F> p;
+        if (z.is_zero()) {
+            p.inf = true;
+            p.x = F::zero();
+            p.y = F::zero();
+        } else {
+            F pre = FW::load(a.prefix + e, n);
+            F zinv = fp_mul(inv, pre);
+            inv = fp_mul(inv, z);
+            Jac<F> j;
+            j.X = FW::load(a.jac + e, n);
+            j.Y = FW::load(a.jac + (uint64_t)FW::W * n + e, n);
+            p = jac_to_affine_with_zinv(j, zinv);
+        }
+        encode_point<G>(a.out + e * owords, a.out_compressed != 0, p);
+        if (e < T) break;
+    }
+}
+
+// ---- write_batch of already-affine elements (decompress / verify re-emit) ------------------------
+struct EncodeArgs {
+    const uint32_t* aff;
+    const uint8_t* inf;
+    uint64_t n;
+    uint32_t* out;
+    int out_compressed;
+};
+
+template <class G>
+__global__ void __launch_bounds__(128) k_encode(EncodeArgs a) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int ow = (a.out_compressed ? G::CSIZE : G::USIZE) / 4;
+    Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
+    encode_point<G>(a.out + i * ow, a.out_compressed != 0, p);
+}
+
+// ---- p.mul_bigint(r).is_zero() for every element (setup-utils/src/elements.rs:138-142) -----------
+struct SubgroupArgs {
+    const uint32_t* aff;
+    const uint8_t* inf;
+    uint64_t n;
+    unsigned long long* status;
+};
+
+template <class G>
+__global__ void __launch_bounds__(128) k_subgroup(SubgroupArgs a) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
+    if (!in_subgroup_rmul<G>(p)) report(a.status, i, ERR_INCORRECT_SUBGROUP);
+}
+
+// ---- function table seen by api.cu -------------------------------------------------------------
+struct GroupOps {
+    int usize, csize;      // serialized element sizes
+    int fr_words;          // scalar limbs (u32)
+    int fr_bytes;          // canonical scalar bytes
+    int coord_words;       // FW
+    void (*prepare_scalars)(const uint32_t* tau_le, const uint32_t* coeff_le, uint32_t* tab, uint32_t* coeff_m,
+                            cudaStream_t);
+    void (*powers)(const uint32_t* tab, uint64_t start, uint64_t n, uint32_t* out, cudaStream_t);
+    void (*decode)(const DecodeArgs&, cudaStream_t);
+    void (*scalar_mul)(const ScalarMulArgs&, cudaStream_t);
+    void (*normalize_encode)(const NormalizeArgs&, cudaStream_t);
+    void (*encode)(const EncodeArgs&, cudaStream_t);
+    void (*subgroup)(const SubgroupArgs&, cudaStream_t);
+};
+
+template <class G>
+struct GroupLaunch {
+    using FrP = typename G::Fr::Params;
+    static void prepare_scalars(const uint32_t* tau_le, const uint32_t* coeff_le, uint32_t* tab, uint32_t* coeff_m,
+                                cudaStream_t s) {
+        k_prepare_scalars<FrP><<<1, 32, 0, s>>>(tau_le, coeff_le, tab, coeff_m);
+    }
+    static void powers(const uint32_t* tab, uint64_t start, uint64_t n, uint32_t* out, cudaStream_t s) {
+        if (!n) return;
+        k_powers<FrP><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(tab, start, n, out);
+    }
+    static void scalar_mul(const ScalarMulArgs& a, cudaStream_t s) {
+        if (!a.n) return;
+        k_scalar_mul<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+    }
+    static void normalize_encode(const NormalizeArgs& a, cudaStream_t s) {
+        if (!a.n) return;
+        k_normalize_encode<G><<<(unsigned)((a.threads + 127) / 128), 128, 0, s>>>(a);
+    }
+    static void decode(const DecodeArgs& a, cudaStream_t s) {
+        if (!a.n) return;
+        k_decode<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+    }
+    static void encode(const EncodeArgs& a, cudaStream_t s) {
+        if (!a.n) return;
+        k_encode<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+    }
+    static void subgroup(const SubgroupArgs& a, cudaStream_t s) {
+        if (!a.n) return;
+        k_subgroup<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+    }
+    static GroupOps ops() {
+        GroupOps o;
+        o.usize = G::USIZE;
+        o.csize = G::CSIZE;
+        o.fr_words = FrP::N;
+        o.fr_bytes = (FrP::BITS + 7) / 8;
+        o.coord_words = FieldWords<typename G::F>::W;
+        o.prepare_scalars = &prepare_scalars;
+        o.powers = &powers;
+        o.scalar_mul = &scalar_mul;
+        o.normalize_encode = &normalize_encode;
+        o.decode = &decode;
+        o.encode = &encode;
+        o.subgroup = &subgroup;
+        return o;
+    }
+};
+
+const GroupOps& ops_bls377_g1();
+const GroupOps& ops_bls377_g2();
+const GroupOps& ops_bw6_g1();
+const GroupOps& ops_bw6_g2();
+
+}  // namespace ss

@@ -1,0 +1,251 @@
+"""ctypes binding of libsnarksetup_b200.so (include/snark_setup_b200.h).
+
+Names, argument meaning and error behaviour follow the reference's Rust API so the parity tests read
+like the reference's own tests (phase1/src/computation.rs:311-538, setup-utils/src/io/mod.rs:23-121).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+lib_path = os.path.join(_CSRC, "libsnarksetup_b200.so")
+
+BLS12_377, BW6_761 = 0, 1
+G1, G2 = 0, 1
+CHECK_FULL, CHECK_ONLY_NON_ZERO, CHECK_ONLY_IN_GROUP, CHECK_NO = 0, 1, 2, 3
+SUBGROUP_AUTO, SUBGROUP_DIRECT, SUBGROUP_BATCHED, SUBGROUP_NO = 0, 1, 2, 3
+MODE_FULL, MODE_CHUNKED = 0, 1
+GROTH16, MARLIN = 0, 1
+
+
+class SetupError(Exception):
+    """setup_utils::Error (setup-utils/src/errors.rs:11-38)."""
+
+    def __init__(self, msg="", index=0, expected=0, got=0):
+        super().__init__(msg)
+        self.index, self.expected, self.got = index, expected, got
+
+
+class InvalidData(SetupError): pass          # noqa: E701
+class UnexpectedFlags(SetupError): pass      # noqa: E701
+class PointAtInfinity(SetupError): pass      # noqa: E701
+class IncorrectSubgroup(SetupError): pass    # noqa: E701
+class InvalidLength(SetupError): pass        # noqa: E701
+class InvalidChunk(SetupError): pass         # noqa: E701
+class BatchTooSmall(SetupError): pass        # noqa: E701
+class InvalidArgument(SetupError): pass      # noqa: E701
+class DeviceError(SetupError): pass          # noqa: E701
+
+
+_ERRORS = {1: InvalidData, 2: UnexpectedFlags, 3: PointAtInfinity, 4: IncorrectSubgroup, 5: InvalidLength,
+           6: InvalidChunk, 7: BatchTooSmall, 8: InvalidArgument, 9: DeviceError}
+
+
+class _ErrInfo(C.Structure):
+    _fields_ = [("code", C.c_int), ("index", C.c_uint64), ("expected", C.c_uint64), ("got", C.c_uint64),
+                ("message", C.c_char * 160)]
+
+
+class _P1Params(C.Structure):
+    _fields_ = [("curve", C.c_int), ("proving_system", C.c_int), ("contribution_mode", C.c_int),
+                ("chunk_index", C.c_uint64), ("chunk_size", C.c_uint64), ("total_size_in_log2", C.c_uint32),
+                ("batch_size", C.c_uint64)]
+
+
+class _P1Sizes(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("powers_length", "powers_g1_length", "g1_chunk_size", "other_chunk_size",
+                                          "accumulator_size", "contribution_size", "public_key_size", "hash_size")]
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-j8", "-C", _CSRC], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libsnarksetup_b200.so failed")
+    return lib_path
+
+
+_lib = None
+
+
+def lib():
+    """The loaded CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path):
+            raise DeviceError(f"{lib_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                              "there is no CPU fallback")
+        L = C.CDLL(lib_path)
+        L.ss_version.restype = C.c_char_p
+        L.ss_element_size.restype = C.c_size_t
+        L.ss_scalar_size.restype = C.c_size_t
+        L.ss_last_error.argtypes = [C.POINTER(_ErrInfo)]
+        L.ss_generate_powers_of_tau.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.ss_apply_powers.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t,
+                                      C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p]
+        L.ss_batch_exp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_char_p]
+        L.ss_batch_mul.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_char_p]
+        L.ss_transcode.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t]
+        L.ss_check_subgroup.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
+        L.ss_phase1_sizes_of.argtypes = [C.POINTER(_P1Params), C.POINTER(_P1Sizes)]
+        L.ss_phase1_computation.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                            C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.ss_phase1_computation_dev.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
+                                                C.c_void_p]
+        L.ss_init.argtypes = [C.POINTER(C.c_int), C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    info = _ErrInfo()
+    lib().ss_last_error(C.byref(info))
+    cls = _ERRORS.get(rc, SetupError)
+    raise cls(info.message.decode(errors="replace"), info.index, info.expected, info.got)
+
+
+def init(devices=None):
+    devices = list(devices or [])
+    arr = (C.c_int * max(1, len(devices)))(*devices)
+    _check(lib().ss_init(arr, len(devices)))
+
+
+def element_size(curve, group, compressed):
+    return lib().ss_element_size(curve, group, int(bool(compressed)))
+
+
+def scalar_size(curve):
+    return lib().ss_scalar_size(curve)
+
+
+def _scalar(curve, v):
+    if v is None:
+        return None
+    if isinstance(v, int):
+        return v.to_bytes(scalar_size(curve), "little")
+    return bytes(v)
+
+
+def _buf(b):
+    """(ctypes pointer, keepalive) for bytes / bytearray / memoryview / numpy arrays."""
+    if isinstance(b, bytes):
+        return C.cast(C.c_char_p(b), C.c_void_p), b
+    if isinstance(b, bytearray):
+        arr = (C.c_char * len(b)).from_buffer(b)
+        return C.cast(arr, C.c_void_p), arr
+    if hasattr(b, "ctypes"):  # numpy
+        return C.c_void_p(b.ctypes.data), b
+    mv = memoryview(b)
+    arr = (C.c_char * mv.nbytes).from_buffer(mv)
+    return C.cast(arr, C.c_void_p), arr
+
+
+def generate_powers_of_tau(curve, tau, start, end):
+    """setup-utils/src/helpers.rs:32-37 -> list of ints."""
+    n = max(0, end - start)
+    fb = scalar_size(curve)
+    out = C.create_string_buffer(max(1, n * fb))
+    _check(lib().ss_generate_powers_of_tau(curve, _scalar(curve, tau), start, end, out))
+    return [int.from_bytes(out.raw[i * fb:(i + 1) * fb], "little") for i in range(n)]
+
+
+def apply_powers(curve, group, inp, in_compressed, in_check, out_compressed, n, *, powers=None, tau=None,
+                 first_power=0, coeff=None):
+    """phase1/src/helpers/buffers.rs:77-97 on a slice that starts at element 0 of `inp`. Returns bytes."""
+    fb = scalar_size(curve)
+    osz = element_size(curve, group, out_compressed)
+    out = bytearray(n * osz)
+    pin, k1 = _buf(inp)
+    pout, k2 = _buf(out) if n else (None, None)
+    pw = None
+    if powers is not None:
+        pw = b"".join(int(p).to_bytes(fb, "little") for p in powers)
+        if len(powers) != n:
+            raise InvalidLength("powers", 0, n, len(powers))
+    ppw, k3 = _buf(pw) if pw else (None, None)
+    _check(lib().ss_apply_powers(curve, group, pin, int(in_compressed), in_check, pout, int(out_compressed), n, ppw,
+                                 _scalar(curve, tau), first_power, _scalar(curve, coeff)))
+    return bytes(out)
+
+
+def batch_exp(curve, group, bases: bytearray, exps, coeff=None):
+    """setup-utils/src/helpers.rs:75-140; `bases` = uncompressed elements, updated in place."""
+    fb = scalar_size(curve)
+    usz = element_size(curve, group, False)
+    n = len(bases) // usz
+    ex = b"".join(int(e).to_bytes(fb, "little") for e in exps)
+    pb, k1 = _buf(bases) if n else (None, None)
+    pe, k2 = _buf(ex) if ex else (None, None)
+    _check(lib().ss_batch_exp(curve, group, pb, n, pe, len(exps), _scalar(curve, coeff)))
+
+
+def batch_mul(curve, group, bases: bytearray, coeff):
+    """setup-utils/src/helpers.rs:56-59."""
+    usz = element_size(curve, group, False)
+    n = len(bases) // usz
+    pb, k1 = _buf(bases) if n else (None, None)
+    _check(lib().ss_batch_mul(curve, group, pb, n, _scalar(curve, coeff)))
+
+
+def transcode(curve, group, inp, in_compressed, check, out_compressed, n=None, want_output=True):
+    """read_batch + write_batch (setup-utils/src/io/{read,write}.rs)."""
+    isz = element_size(curve, group, in_compressed)
+    osz = element_size(curve, group, out_compressed)
+    if n is None:
+        n = len(inp) // isz
+    out = bytearray(n * osz) if want_output else None
+    pin, k1 = _buf(inp) if n else (None, None)
+    pout, k2 = _buf(out) if (want_output and n) else (None, None)
+    _check(lib().ss_transcode(curve, group, pin, int(in_compressed), check, pout, int(out_compressed), n))
+    return bytes(out) if want_output else None
+
+
+def check_subgroup(curve, group, inp, compressed, mode=SUBGROUP_AUTO):
+    """setup-utils/src/elements.rs:123-150."""
+    sz = element_size(curve, group, compressed)
+    n = len(inp) // sz
+    pin, k1 = _buf(inp) if n else (None, None)
+    _check(lib().ss_check_subgroup(curve, group, pin, int(compressed), n, mode))
+
+
+class Phase1Parameters:
+    """phase1/src/objects/parameters.rs:115-294."""
+
+    def __init__(self, curve, power, batch_size, mode=MODE_FULL, chunk_index=0, chunk_size=0, proving_system=GROTH16):
+        self.c = _P1Params(curve, proving_system, mode, chunk_index, chunk_size, power, batch_size)
+        z = _P1Sizes()
+        _check(lib().ss_phase1_sizes_of(C.byref(self.c), C.byref(z)))
+        for n, _ in _P1Sizes._fields_:
+            setattr(self, n, getattr(z, n))
+        self.curve = curve
+
+    def get_length(self, compressed):
+        return self.contribution_size - self.public_key_size if compressed else self.accumulator_size
+
+
+def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
+                       tau, alpha, beta):
+    """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place."""
+    pin, k1 = _buf(inp)
+    pout, k2 = _buf(out)
+    cv = params.curve
+    _check(lib().ss_phase1_computation(C.byref(params.c), pin, len(inp), pout, len(out), int(compressed_input),
+                                       int(compressed_output), check_input, _scalar(cv, tau), _scalar(cv, alpha),
+                                       _scalar(cv, beta)))
+
+
+def phase1_computation_dev(params: Phase1Parameters, d_in, in_len, d_out, out_len, compressed_input,
+                           compressed_output, check_input, tau, alpha, beta, stream=0):
+    """Same, on device pointers (ints) of the current CUDA device."""
+    cv = params.curve
+    _check(lib().ss_phase1_computation_dev(C.byref(params.c), d_in, in_len, d_out, out_len, int(compressed_input),
+                                           int(compressed_output), check_input, _scalar(cv, tau), _scalar(cv, alpha),
+                                           _scalar(cv, beta), stream))

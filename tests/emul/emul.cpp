@@ -1,0 +1,162 @@
+// TEST INFRASTRUCTURE: host build of the device math headers (ptx.cuh's carry-flag emulation), so
+// the limb-level algorithms can be checked against oracle/pyref.py on a box without a GPU.
+// Never linked into the product library.
+#include <cstring>
+#include "../../snark-setup_b200/csrc/codec.cuh"
+
+using namespace ss;
+
+template <class P>
+static Fp<P> load_raw(const uint8_t* b) {
+    Fp<P> r;
+    memcpy(r.l, b, 4 * P::N);
+    return r;
+}
+template <class P>
+static void store_raw(uint8_t* b, const Fp<P>& a) {
+    memcpy(b, a.l, 4 * P::N);
+}
+
+// op: 0 mul 1 add 2 sub 3 neg 4 inv 5 sqrt (returns 1 if no root) 6 sqr
+template <class P>
+static int fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fp<P> x = fp_to_mont(load_raw<P>(a)), y = fp_to_mont(load_raw<P>(b)), r;
+    int rc = 0;
+    switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_neg(x); break;
+        case 4: r = fp_inv(x); break;
+        case 5: rc = fp_sqrt(x, r) ? 0 : 1; if (rc) r = Fp<P>::zero(); break;
+        case 6: r = fp_sqr(x); break;
+        default: return -1;
+    }
+    store_raw<P>(out, fp_from_mont(r));
+    return rc;
+}
+
+template <class P>
+static int fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fp2<P> x{fp_to_mont(load_raw<P>(a)), fp_to_mont(load_raw<P>(a + 4 * P::N))};
+    Fp2<P> y{fp_to_mont(load_raw<P>(b)), fp_to_mont(load_raw<P>(b + 4 * P::N))};
+    Fp2<P> r;
+    int rc = 0;
+    switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_neg(x); break;
+        case 4: r = fp_inv(x); break;
+        case 5: rc = fp_sqrt(x, r) ? 0 : 1; if (rc) r = Fp2<P>::zero(); break;
+        case 6: r = fp_sqr(x); break;
+        default: return -1;
+    }
+    store_raw<P>(out, fp_from_mont(r.c0));
+    store_raw<P>(out + 4 * P::N, fp_from_mont(r.c1));
+    return rc;
+}
+
+template <class G>
+static int point_mul(const uint8_t* in, int in_compressed, int check, const uint8_t* scalar, int nbits,
+                     uint8_t* out, int out_compressed) {
+    using F = typename G::F;
+    Affine<F> p;
+    uint32_t w[64];
+    memcpy(w, in, in_compressed ? G::CSIZE : G::USIZE);
+    int e = decode_point<G>(w, in_compressed != 0, check, p);
+    if (e) return e;
+    uint32_t s[16] = {0};
+    memcpy(s, scalar, (nbits + 7) / 8);
+    Jac<F> r = jac_mul_bits<F>(p, [&](int i) { return s[i]; }, nbits);
+    Affine<F> a;
+    if (r.is_identity()) {
+        a.inf = true;
+        a.x = F::zero();
+        a.y = F::zero();
+    } else {
+        a = jac_to_affine_with_zinv(r, fp_inv(r.Z));
+    }
+    uint32_t o[64];
+    encode_point<G>(o, out_compressed != 0, a);
+    memcpy(out, o, out_compressed ? G::CSIZE : G::USIZE);
+    return 0;
+}
+
+// out = P + Q via jac_add / jac_madd (which: 0 madd, 1 add(jac,jac) with randomised Z)
+template <class G>
+static int point_add(const uint8_t* pa, const uint8_t* pb, int which, uint8_t* out) {
+    using F = typename G::F;
+    Affine<F> p, q;
+    uint32_t w[64];
+    memcpy(w, pa, G::USIZE);
+    if (int e = decode_point<G>(w, false, CHECK_NO, p)) return e;
+    memcpy(w, pb, G::USIZE);
+    if (int e = decode_point<G>(w, false, CHECK_NO, q)) return e;
+    Jac<F> jp = p.inf ? Jac<F>::identity() : Jac<F>{p.x, p.y, F::one()};
+    Jac<F> r;
+    if (which == 0) {
+        // give jp a non-trivial Z first: (X*4, Y*8, 2)
+        if (!p.inf) {
+            F two = fp_dbl(F::one());
+            jp.X = fp_mul(p.x, fp_sqr(two));
+            jp.Y = fp_mul(p.y, fp_mul(fp_sqr(two), two));
+            jp.Z = two;
+        }
+        r = jac_madd(jp, q);
+    } else {
+        Jac<F> jq = q.inf ? Jac<F>::identity() : Jac<F>{q.x, q.y, F::one()};
+        if (!q.inf) {
+            F three = fp_add(fp_dbl(F::one()), F::one());
+            jq.X = fp_mul(q.x, fp_sqr(three));
+            jq.Y = fp_mul(q.y, fp_mul(fp_sqr(three), three));
+            jq.Z = three;
+        }
+        r = jac_add(jp, jq);
+    }
+    Affine<F> a;
+    if (r.is_identity()) {
+        a.inf = true;
+        a.x = F::zero();
+        a.y = F::zero();
+    } else {
+        a = jac_to_affine_with_zinv(r, fp_inv(r.Z));
+    }
+    uint32_t o[64];
+    encode_point<G>(o, false, a);
+    memcpy(out, o, G::USIZE);
+    return 0;
+}
+
+extern "C" {
+// field: 0 Bls377Fq, 1 Bls377Fr, 2 Bw6Fq, 3 Bls377Fq2
+int emul_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    switch (field) {
+        case 0: return fp_op<Bls377Fq>(op, a, b, out);
+        case 1: return fp_op<Bls377Fr>(op, a, b, out);
+        case 2: return fp_op<Bw6Fq>(op, a, b, out);
+        case 3: return fp2_op<Bls377Fq>(op, a, b, out);
+    }
+    return -1;
+}
+// group: 0 bls g1, 1 bls g2, 2 bw6 g1, 3 bw6 g2
+int emul_point_mul(int group, const uint8_t* in, int in_compressed, int check, const uint8_t* scalar, int nbits,
+                   uint8_t* out, int out_compressed) {
+    switch (group) {
+        case 0: return point_mul<Bls377G1>(in, in_compressed, check, scalar, nbits, out, out_compressed);
+        case 1: return point_mul<Bls377G2>(in, in_compressed, check, scalar, nbits, out, out_compressed);
+        case 2: return point_mul<Bw6G1>(in, in_compressed, check, scalar, nbits, out, out_compressed);
+        case 3: return point_mul<Bw6G2>(in, in_compressed, check, scalar, nbits, out, out_compressed);
+    }
+    return -1;
+}
+int emul_point_add(int group, const uint8_t* a, const uint8_t* b, int which, uint8_t* out) {
+    switch (group) {
+        case 0: return point_add<Bls377G1>(a, b, which, out);
+        case 1: return point_add<Bls377G2>(a, b, which, out);
+        case 2: return point_add<Bw6G1>(a, b, which, out);
+        case 3: return point_add<Bw6G2>(a, b, which, out);
+    }
+    return -1;
+}
+}

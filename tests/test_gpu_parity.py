@@ -1,0 +1,146 @@
+"""GPU parity: the CUDA path (through the C ABI) against the pure-Python restatement oracle/pyref.py
+on seeded inputs.  Bit-exact: these are integer/byte computations."""
+import random
+
+import pytest
+
+import pyref as R
+import snark_setup_b200 as S
+
+pytestmark = pytest.mark.gpu
+
+CURVES = [(S.BLS12_377, R.BLS12_377), (S.BW6_761, R.BW6_761)]
+GROUPS = [(cid, cv, gid, g) for cid, cv in CURVES for gid, g in ((S.G1, cv.g1), (S.G2, cv.g2))]
+IDS = [g.name for _, _, _, g in GROUPS]
+
+
+def rand_points(g, n, rng):
+    acc = g.mul(g.gen, rng.randrange(1, g.r))
+    step = g.mul(g.gen, rng.randrange(1, g.r))
+    out = []
+    for _ in range(n):
+        out.append(acc)
+        acc = g.add(acc, step)
+    return out
+
+
+@pytest.mark.parametrize("cid,cv,gid,g", GROUPS, ids=IDS)
+def test_transcode_roundtrip(cid, cv, gid, g):
+    """setup-utils/src/io/mod.rs:33-120: write -> read round trips, compressed and not, + infinity."""
+    rng = random.Random(11)
+    pts = rand_points(g, 70, rng) + [None]
+    for ci in (False, True):
+        buf = g.write_batch(pts, ci)
+        for co in (False, True):
+            got = S.transcode(cid, gid, buf, ci, S.CHECK_NO, co)
+            assert got == g.write_batch(pts, co), (ci, co)
+    with pytest.raises(S.PointAtInfinity):
+        S.transcode(cid, gid, g.write_batch(pts, True), True, S.CHECK_ONLY_NON_ZERO, False)
+    ok = g.write_batch(pts[:-1], True)
+    assert S.transcode(cid, gid, ok, True, S.CHECK_FULL, False) == g.write_batch(pts[:-1], False)
+
+
+@pytest.mark.parametrize("cid,cv,gid,g", GROUPS, ids=IDS)
+def test_decode_errors(cid, cv, gid, g):
+    rng = random.Random(5)
+    pts = rand_points(g, 40, rng)
+    buf = bytearray(g.write_batch(pts, True))
+    bad = bytearray(buf)
+    bad[17 * g.csize + g.csize - 1] |= 0xC0
+    with pytest.raises(S.UnexpectedFlags) as ei:
+        S.transcode(cid, gid, bytes(bad), True, S.CHECK_NO, False)
+    assert ei.value.index == 17
+    bad = bytearray(buf)
+    bad[9 * g.csize:10 * g.csize] = b"\xff" * (g.csize - 1) + b"\x3f"
+    with pytest.raises(S.InvalidData) as ei:
+        S.transcode(cid, gid, bytes(bad), True, S.CHECK_NO, False)
+    assert ei.value.index == 9
+    # an x whose x^3+b has no square root
+    x = 2
+    while True:
+        xx = x if g.F.degree == 1 else (x, 1)
+        try:
+            g.decode(g.F.to_bytes(xx, 0, 2), True, R.NO)
+            x += 1
+        except R.InvalidData:
+            break
+    bad = bytearray(buf)
+    bad[3 * g.csize:4 * g.csize] = g.F.to_bytes(xx, 0, 2)
+    with pytest.raises(S.InvalidData) as ei:
+        S.transcode(cid, gid, bytes(bad), True, S.CHECK_NO, False)
+    assert ei.value.index == 3
+
+
+@pytest.mark.parametrize("cid,cv,gid,g", GROUPS, ids=IDS)
+def test_apply_powers_matches_oracle(cid, cv, gid, g):
+    """phase1/src/computation.rs:323-445: output == batch_exp(generate_powers_of_tau) per element."""
+    rng = random.Random(2024)
+    n = 96
+    pts = rand_points(g, n, rng)
+    pts[5] = None
+    tau, coeff = rng.randrange(cv.r), rng.randrange(cv.r)
+    start = 1000003
+    powers = R.generate_powers_of_tau(cv, tau, start, start + n)
+    assert S.generate_powers_of_tau(cid, tau, start, start + n) == powers
+    for cf in (None, coeff):
+        want_pts = R.batch_exp(g, pts, powers, cf)
+        for ci in (False, True):
+            inp = g.write_batch(pts, ci)
+            for co in (False, True):
+                got = S.apply_powers(cid, gid, inp, ci, S.CHECK_NO, co, n, tau=tau, first_power=start, coeff=cf)
+                assert got == g.write_batch(want_pts, co), (cf is not None, ci, co)
+    # explicit scalars (batch_exp), in place, incl. the edge scalars 0, 1, r-1
+    exps = [0, 1, cv.r - 1] + [rng.randrange(cv.r) for _ in range(n - 3)]
+    bases = bytearray(g.write_batch(pts, False))
+    S.batch_exp(cid, gid, bases, exps, coeff)
+    assert bytes(bases) == g.write_batch(R.batch_exp(g, pts, exps, coeff), False)
+    with pytest.raises(S.InvalidLength):
+        S.batch_exp(cid, gid, bases, exps[:-1])
+    # batch_mul (phase2 delta^-1)
+    bases = bytearray(g.write_batch(pts, False))
+    S.batch_mul(cid, gid, bases, coeff)
+    assert bytes(bases) == g.write_batch(R.batch_mul(g, pts, coeff), False)
+
+
+@pytest.mark.parametrize("cid,cv,gid,g", GROUPS, ids=IDS)
+def test_check_subgroup(cid, cv, gid, g):
+    rng = random.Random(77)
+    pts = rand_points(g, 33, rng)
+    S.check_subgroup(cid, gid, g.write_batch(pts, True), True)
+    S.check_subgroup(cid, gid, g.write_batch(pts, False), False)
+    # a curve point outside the r-torsion: random x on the curve (cofactor > 1 for all four groups)
+    x = 5
+    while True:
+        xx = x if g.F.degree == 1 else (x, 3)
+        try:
+            P = g.decode(g.F.to_bytes(xx, 0, 2), True, R.NO)
+            if not g.in_subgroup(P):
+                break
+        except R.InvalidData:
+            pass
+        x += 1
+    pts[20] = P
+    with pytest.raises(S.IncorrectSubgroup) as ei:
+        S.check_subgroup(cid, gid, g.write_batch(pts, True), True)
+    assert ei.value.index == 20
+    with pytest.raises(S.InvalidData):
+        S.transcode(cid, gid, g.write_batch(pts, True), True, S.CHECK_FULL, False)
+
+
+@pytest.mark.parametrize("power,batch", [(3, 4), (5, 16)])
+def test_phase1_computation_bls12_377(power, batch):
+    """Phase1::computation vs the oracle's restatement, all compression combinations."""
+    cv = R.BLS12_377
+    rng = random.Random(power)
+    rp = R.Phase1Parameters(cv, power, batch)
+    sp = S.Phase1Parameters(S.BLS12_377, power, batch)
+    assert (sp.accumulator_size, sp.contribution_size) == (rp.accumulator_size, rp.contribution_size)
+    t0, a0, b0 = (rng.randrange(1, cv.r) for _ in range(3))
+    tau, alpha, beta = (rng.randrange(1, cv.r) for _ in range(3))
+    for cin in (False, True):
+        acc = bytes(R.phase1_computation(rp, bytes(R.phase1_initialization(rp, False)), False, cin, R.NO, t0, a0, b0))
+        for cout in (False, True):
+            want = R.phase1_computation(rp, acc, cin, cout, R.NO, tau, alpha, beta)
+            out = bytearray(sp.get_length(cout))
+            S.phase1_computation(sp, acc, out, cin, cout, S.CHECK_NO, tau, alpha, beta)
+            assert bytes(out) == bytes(want), (cin, cout)
