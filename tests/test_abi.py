@@ -1,0 +1,60 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/*.h declares, and its host-only
+entry points (size arithmetic) agree with the reference's formulas; compute calls fail loudly (no CPU
+fallback) when no device exists."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import pyref as R
+import snark_setup_b200 as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "snark_setup_b200.h")).read()
+    names = sorted(set(re.findall(r"^(?:int|void|size_t|const char\*)\s+(ss_[a-z0-9_]+)\s*\(", hdr, re.M)))
+    assert len(names) >= 15
+    L = ctypes.CDLL(S.lib_path)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+
+
+def test_sizes_match_reference_formulas():
+    assert [S.element_size(S.BLS12_377, g, c) for g in (0, 1) for c in (0, 1)] == [96, 48, 192, 96]
+    assert [S.element_size(S.BW6_761, g, c) for g in (0, 1) for c in (0, 1)] == [192, 96, 192, 96]
+    assert (S.scalar_size(S.BLS12_377), S.scalar_size(S.BW6_761)) == (32, 48)
+    for cid, cv in ((S.BLS12_377, R.BLS12_377), (S.BW6_761, R.BW6_761)):
+        for k, bs, mode, ci, cs in ((10, 256, 0, 0, 0), (20, 256, 0, 0, 0), (4, 8, 1, 0, 8), (4, 8, 1, 1, 8), (4, 8, 1, 2, 8),
+                                    (4, 8, 1, 3, 8), (5, 7, 1, 2, 20)):
+            a = S.Phase1Parameters(cid, k, bs, mode, ci, cs)
+            b = R.Phase1Parameters(cv, k, bs, mode, ci, cs)
+            for f in ("powers_length", "powers_g1_length", "g1_chunk_size", "other_chunk_size", "accumulator_size",
+                      "contribution_size", "public_key_size", "hash_size"):
+                assert getattr(a, f) == getattr(b, f), (cv.name, k, mode, ci, f)
+
+
+def test_argument_errors_are_reported_without_device():
+    with pytest.raises(S.InvalidLength) as ei:
+        S.batch_exp(S.BLS12_377, S.G1, bytearray(96 * 3), [1, 2])
+    assert (ei.value.expected, ei.value.got) == (3, 2)
+    with pytest.raises(S.SetupError):
+        S.Phase1Parameters(7, 10, 256)
+
+
+@pytest.mark.skipif(_have_gpu(), reason="box has a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(S.DeviceError):
+        S.generate_powers_of_tau(S.BLS12_377, 5, 0, 4)
+    with pytest.raises(S.DeviceError):
+        S.apply_powers(S.BLS12_377, S.G1, bytes(96), False, S.CHECK_NO, True, 1, tau=3)
