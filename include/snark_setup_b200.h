@@ -77,6 +77,21 @@ int ss_device_count(void);
 void ss_last_error(ss_error_info* out);
 const char* ss_version(void);
 
+/* Per-kernel timing, the engine's counterpart of the reference's `tracing` spans and its
+ * Instant timer around the subgroup loop (phase1/src/computation.rs:26,56;
+ * phase1/src/helpers/accumulator.rs:110,140): when enabled, every kernel launch is bracketed by CUDA
+ * events on its own stream.  ss_profile_launches() counts launches whether or not timing is on. */
+typedef struct {
+    char name[64];     /* e.g. "k_scalar_mul<bls12_377.g1>" */
+    uint64_t launches; /* kernel launches */
+    uint64_t elements; /* group elements processed by those launches */
+    double ms;         /* summed device time */
+} ss_profile_entry;
+void ss_profile_enable(int on);
+void ss_profile_reset(void);
+uint64_t ss_profile_launches(void);
+int ss_profile_read(ss_profile_entry* out, int max_entries);
+
 /* buffer_size::<C>(compression) — setup-utils/src/io/mod.rs:13-15 */
 size_t ss_element_size(int curve, int group, int compressed);
 size_t ss_scalar_size(int curve);

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +56,71 @@ const GroupOps* group_ops(int curve, int group) {
     if (curve == SS_CURVE_BLS12_377) return group == SS_G1 ? &ops_bls377_g1() : group == SS_G2 ? &ops_bls377_g2() : nullptr;
     if (curve == SS_CURVE_BW6_761) return group == SS_G1 ? &ops_bw6_g1() : group == SS_G2 ? &ops_bw6_g2() : nullptr;
     return nullptr;
+}
+
+// ---- per-kernel timing (ss_profile_*) -----------------------------------------------------------
+// When enabled every launch is bracketed by two CUDA events recorded on the launching stream; the
+// pairs are resolved after the stream has been synchronised.  bench.py uses this for the per-kernel
+// durations behind `roofline` and for `gpu_launches`.
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+struct ProfAcc {
+    std::string name;
+    uint64_t launches = 0, elements = 0;
+    double ms = 0;
+};
+std::vector<ProfAcc> g_prof;
+struct ProfPending {
+    std::string name;
+    uint64_t elements;
+    cudaEvent_t e0, e1;
+};
+thread_local std::vector<ProfPending> g_prof_pending;
+std::atomic<uint64_t> g_launches{0};
+
+struct ProfScope {
+    bool on;
+    ProfPending p;
+    cudaStream_t s;
+    ProfScope(const char* kind, const char* group, uint64_t elements, cudaStream_t stream) : s(stream) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        on = g_prof_on;
+        if (!on) return;
+        p.name = std::string(kind) + "<" + group + ">";
+        p.elements = elements;
+        cudaEventCreate(&p.e0);
+        cudaEventCreate(&p.e1);
+        cudaEventRecord(p.e0, s);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(p.e1, s);
+        g_prof_pending.push_back(p);
+    }
+};
+
+// call after the streams used since the last flush have been synchronised
+void prof_flush() {
+    if (g_prof_pending.empty()) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& p : g_prof_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.e1) == cudaSuccess) cudaEventElapsedTime(&ms, p.e0, p.e1);
+        cudaEventDestroy(p.e0);
+        cudaEventDestroy(p.e1);
+        ProfAcc* a = nullptr;
+        for (auto& x : g_prof)
+            if (x.name == p.name) a = &x;
+        if (!a) {
+            g_prof.push_back(ProfAcc());
+            a = &g_prof.back();
+            a->name = p.name;
+        }
+        a->launches++;
+        a->elements += p.elements;
+        a->ms += ms;
+    }
+    g_prof_pending.clear();
 }
 
 // ---- devices ------------------------------------------------------------------------------------
@@ -275,7 +341,7 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
         da.aff = aff;
         da.inf = inf;
         da.status = d_status + t;
-        o.decode(da, s);
+        { ProfScope ps("k_decode", o.name, cnt, s); o.decode(da, s); }
         ScalarMulArgs a;
         a.aff = aff;
         a.inf = inf;
@@ -286,7 +352,7 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
         a.coeff_m = j.d_coeff_m;
         a.has_coeff = j.has_coeff;
         a.jac = jac;
-        o.scalar_mul(a, s);
+        { ProfScope ps("k_scalar_mul", o.name, cnt, s); o.scalar_mul(a, s); }
         NormalizeArgs na;
         na.jac = jac;
         na.n = cnt;
@@ -294,13 +360,14 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
         na.out = reinterpret_cast<uint32_t*>(d_out);
         na.out_compressed = j.out_c;
         na.threads = normalize_threads(cnt);
-        o.normalize_encode(na, s);
+        { ProfScope ps("k_normalize_encode", o.name, cnt, s); o.normalize_encode(na, s); }
         if (host) CU(cudaMemcpyAsync(j.out + e0 * osz, d_out, cnt * osz, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaGetLastError());
     for (int k = 0; k < nl; k++) CU(cudaStreamSynchronize((!host && user_stream) ? user_stream : lg[k].l->stream));
     if (ev_init) cudaEventDestroy(ev_init);
     CU(cudaMemcpy(st.data(), d_status, ntiles * 8, cudaMemcpyDeviceToHost));
+    prof_flush();
     for (size_t t = 0; t < ntiles && rc == SS_OK; t++) rc = decode_status(st[t], t * T, j.what);
     return rc;
 }
@@ -489,6 +556,34 @@ void ss_shutdown(void) {
     g_inited = false;
 }
 
+void ss_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+}
+
+void ss_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.clear();
+    g_launches.store(0);
+}
+
+uint64_t ss_profile_launches(void) { return g_launches.load(); }
+
+int ss_profile_read(ss_profile_entry* out, int max_entries) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (auto& a : g_prof) {
+        if (n >= max_entries) break;
+        memset(&out[n], 0, sizeof(out[n]));
+        snprintf(out[n].name, sizeof(out[n].name), "%s", a.name.c_str());
+        out[n].launches = a.launches;
+        out[n].elements = a.elements;
+        out[n].ms = a.ms;
+        n++;
+    }
+    return n;
+}
+
 int ss_device_count(void) {
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
@@ -613,19 +708,22 @@ static int transcode_impl(int curve, int group, const uint8_t* in, int in_compre
         CU(cudaMemsetAsync(d_status, 0xff, 16, s));
         CU(cudaMemcpyAsync(bi, in + e0 * isz, cnt * isz, cudaMemcpyHostToDevice, s));
         DecodeArgs da = {reinterpret_cast<const uint32_t*>(bi), in_compressed, check, cnt, aff, inf, d_status};
-        o->decode(da, s);
+        { ProfScope ps("k_decode", o->name, cnt, s); o->decode(da, s); }
         if (rmul_subgroup) {
             SubgroupArgs sa = {aff, inf, cnt, d_status + 1};
+            ProfScope ps("k_subgroup", o->name, cnt, s);
             o->subgroup(sa, s);
         }
         if (out) {
             EncodeArgs ea = {aff, inf, cnt, reinterpret_cast<uint32_t*>(bo), out_compressed};
+            ProfScope ps("k_encode", o->name, cnt, s);
             o->encode(ea, s);
         }
         CU(cudaGetLastError());
         unsigned long long st[2];
         CU(cudaMemcpyAsync(st, d_status, 16, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        prof_flush();
         if ((rc = decode_status(st[0], e0, "read_batch"))) return rc;
         if ((rc = decode_status(st[1], e0, "check_subgroup"))) return rc;
         if (out) {

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(128) k_subgroup(SubgroupArgs a) {
 
 // ---- function table seen by api.cu -------------------------------------------------------------
 struct GroupOps {
+    const char* name;      // e.g. "bls12_377.g1" (profiling labels)
     int usize, csize;      // serialized element sizes
     int fr_words;          // scalar limbs (u32)
     int fr_bytes;          // canonical scalar bytes
@@ -337,6 +338,7 @@ struct GroupLaunch {
     }
     static GroupOps ops() {
         GroupOps o;
+        o.name = G::name();
         o.usize = G::USIZE;
         o.csize = G::CSIZE;
         o.fr_words = FrP::N;

@@ -112,6 +112,34 @@ def _check(rc):
     raise cls(info.message.decode(errors="replace"), info.index, info.expected, info.got)
 
 
+class _ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("launches", C.c_uint64), ("elements", C.c_uint64), ("ms", C.c_double)]
+
+
+def profile_enable(on=True):
+    lib().ss_profile_enable(int(on))
+
+
+def profile_reset():
+    lib().ss_profile_reset()
+
+
+def profile_launches():
+    f = lib().ss_profile_launches
+    f.restype = C.c_uint64
+    return f()
+
+
+def profile_read():
+    """{kernel name: {"launches", "elements", "ms"}} accumulated since the last reset."""
+    arr = (_ProfEntry * 64)()
+    f = lib().ss_profile_read
+    f.argtypes = [C.POINTER(_ProfEntry), C.c_int]
+    n = f(arr, 64)
+    return {arr[i].name.decode(): {"launches": arr[i].launches, "elements": arr[i].elements, "ms": arr[i].ms}
+            for i in range(n)}
+
+
 def init(devices=None):
     devices = list(devices or [])
     arr = (C.c_int * max(1, len(devices)))(*devices)
