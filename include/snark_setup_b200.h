@@ -122,9 +122,35 @@ int ss_transcode(int curve, int group, const uint8_t* in, int in_compressed, int
 /* check_subgroup — setup-utils/src/elements.rs:123-150 on n serialized elements. */
 int ss_check_subgroup(int curve, int group, const uint8_t* in, int compressed, size_t n, int subgroup_mode);
 
+/* merge_pairs — setup-utils/src/helpers.rs:371-384: (s, sx) = (sum rho_i v1_i, sum rho_i v2_i), both
+ * returned as UNCOMPRESSED elements for the caller's check_same_ratio (helpers.rs:410-424; the 2
+ * pairings stay on the host).  Randomness: `rho` = n explicit scalars (tests / deterministic callers)
+ * or, when NULL, rho_i = first 128 bits of ChaCha20(key = rho_seed[32], counter = i) generated on the
+ * device (the reference draws full-width scalars from thread_rng, helpers.rs:373-376; 128 bits keep
+ * the soundness error at 2^-128).  Phase 2 uses it for the H and L queries
+ * (phase2/src/parameters.rs:393-407, phase2/src/chunked_groth16.rs:521-566). */
+int ss_merge_pairs(int curve, int group, const uint8_t* v1, const uint8_t* v2, int compressed, int check, size_t n,
+                   const uint8_t* rho, const uint8_t* rho_seed, uint8_t* out_s, uint8_t* out_sx);
+
+/* power_pairs — setup-utils/src/helpers.rs:388-390: merge_pairs(v[..n-1], v[1..]); n-1 scalars. */
+int ss_power_pairs(int curve, int group, const uint8_t* v, int compressed, int check, size_t n, const uint8_t* rho,
+                   const uint8_t* rho_seed, uint8_t* out_s, uint8_t* out_sx);
+
 /* -------------------------------------------------------------------------------------------- */
 /* phase1 helpers                                                                               */
 /* -------------------------------------------------------------------------------------------- */
+/* check_elements_are_nonzero_and_in_prime_order_subgroup + check_power_ratios(_g2) + re-emit —
+ * phase1/src/helpers/accumulator.rs:95-145,56-91 and the write_batch of
+ * phase1/src/verification.rs:271-274, fused over ONE decode of the n elements:
+ *   - decode with CheckForCorrectness::OnlyNonZero (infinity => SS_ERR_POINT_AT_INFINITY)
+ *   - unless subgroup_mode == SS_SUBGROUP_NO: every element must satisfy r*P = O
+ *     (else SS_ERR_INCORRECT_SUBGROUP)
+ *   - do_ratio: (out_s, out_sx) = power_pairs of the n elements (see ss_merge_pairs for rho)
+ *   - out != NULL: the elements re-encoded with out_compressed. */
+int ss_check_and_ratio(int curve, int group, const uint8_t* in, int in_compressed, size_t n, int subgroup_mode,
+                       int do_ratio, const uint8_t* rho, const uint8_t* rho_seed, uint8_t* out, int out_compressed,
+                       uint8_t* out_s, uint8_t* out_sx);
+
 /* apply_powers — phase1/src/helpers/buffers.rs:77-97, fused with generate_powers_of_tau.
  * in/out point at element `start` of the vector (the caller has applied start*size already);
  * n = end - start.  Scalars: `powers` (n explicit scalars) when non-NULL, otherwise
@@ -163,6 +189,26 @@ int ss_phase1_computation(const ss_phase1_params* p, const uint8_t* input, size_
 int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, size_t input_len, void* d_output,
                               size_t output_len, int compressed_input, int compressed_output, int check_input,
                               const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, void* stream);
+
+/* The per-vector hot loop of Phase1::verification — phase1/src/verification.rs:217-411 (Groth16) —
+ * over a whole response: for tau_g1, tau_g2, alpha_g1, beta_g1: nonzero + subgroup check, the
+ * power_pairs (s, sx) for the caller's check_same_ratio, and the vector re-encoded into
+ * new_challenge (NULL: aggregate_verification style, no re-emit, verification.rs:505-769);
+ * beta_g2 is validated and re-emitted too (verification.rs:199-201).
+ * `pairs`: 4 x (s || sx), uncompressed, in the order tau_g1, tau_g2, alpha_g1, beta_g1
+ * (2*g1, 2*g2, 2*g1, 2*g1 uncompressed sizes).  The O(1) proof-of-knowledge / generator /
+ * before-after pairing checks on the first elements (verification.rs:83-213) and the 8 pairings on
+ * `pairs` stay with the caller.  The 64-byte hash prefix of new_challenge is not written. */
+int ss_phase1_verification_vectors(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
+                                   int compressed_output, uint8_t* new_challenge, size_t new_challenge_len,
+                                   int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                   const uint8_t* rho_seed, uint8_t* pairs);
+
+/* Same on buffers resident in device memory (`pairs` and rho_seed stay host pointers). */
+int ss_phase1_verification_vectors_dev(const ss_phase1_params* p, const void* d_output, size_t output_len,
+                                       int compressed_output, void* d_new_challenge, size_t new_challenge_len,
+                                       int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                       const uint8_t* rho_seed, uint8_t* pairs, void* stream);
 
 #ifdef __cplusplus
 }

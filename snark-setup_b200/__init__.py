@@ -29,8 +29,13 @@ from .ffi import (  # noqa: F401
     batch_exp,
     batch_mul,
     build,
+    check_and_ratio,
     check_subgroup,
     element_size,
+    merge_pairs,
+    phase1_verification_vectors,
+    phase1_verification_vectors_dev,
+    power_pairs,
     generate_powers_of_tau,
     lib,
     lib_path,

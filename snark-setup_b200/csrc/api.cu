@@ -24,7 +24,7 @@
 #include <vector>
 
 #include "../../include/snark_setup_b200.h"
-#include "kernels.cuh"
+#include "msm.cuh"
 
 namespace {
 
@@ -526,6 +526,8 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
 }  // namespace
 
 // =====================================================================================================
+#include "api_ratio.inl"
+
 extern "C" {
 
 const char* ss_version(void) { return "snark-setup-b200 0.1 (sm_100a)"; }
@@ -710,12 +712,12 @@ static int transcode_impl(int curve, int group, const uint8_t* in, int in_compre
         DecodeArgs da = {reinterpret_cast<const uint32_t*>(bi), in_compressed, check, cnt, aff, inf, d_status};
         { ProfScope ps("k_decode", o->name, cnt, s); o->decode(da, s); }
         if (rmul_subgroup) {
-            SubgroupArgs sa = {aff, inf, cnt, d_status + 1};
+            SubgroupArgs sa = {aff, inf, cnt, d_status + 1, cnt};
             ProfScope ps("k_subgroup", o->name, cnt, s);
             o->subgroup(sa, s);
         }
         if (out) {
-            EncodeArgs ea = {aff, inf, cnt, reinterpret_cast<uint32_t*>(bo), out_compressed};
+            EncodeArgs ea = {aff, inf, cnt, reinterpret_cast<uint32_t*>(bo), out_compressed, cnt};
             ProfScope ps("k_encode", o->name, cnt, s);
             o->encode(ea, s);
         }

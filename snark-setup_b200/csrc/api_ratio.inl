@@ -1,0 +1,343 @@
+// Included by api.cu (shares its anonymous-namespace helpers): the verification side of the path.
+//
+//   check_elements_are_nonzero_and_in_prime_order_subgroup   phase1/src/helpers/accumulator.rs:95-145
+//   check_power_ratios / check_power_ratios_g2               phase1/src/helpers/accumulator.rs:56-91
+//   merge_pairs / power_pairs                                setup-utils/src/helpers.rs:371-390
+//   per-vector loop of Phase1::verification                  phase1/src/verification.rs:243-411
+//   aggregate_verification                                   phase1/src/verification.rs:505-769
+//   H/L ratio checks of MPCParameters::verify                phase2/src/parameters.rs:393-407
+//
+// The reference decodes every window twice, checks the subgroup, runs two MSMs and re-encodes, window
+// by window, with 2 pairings per window.  Here a vector is decoded ONCE per tile and the same affine
+// scratch feeds the subgroup kernel, the bucket MSM (whose accumulators persist across tiles, so one
+// (s, sx) pair comes out per vector) and the re-encode.  `check_same_ratio` (2 pairings per vector)
+// stays with the caller (helpers.rs:410-424).
+
+namespace {
+
+const MsmOps* msm_ops(int curve, int group) {
+    if (curve == SS_CURVE_BLS12_377) return group == SS_G1 ? &msm_ops_bls377_g1() : group == SS_G2 ? &msm_ops_bls377_g2() : nullptr;
+    if (curve == SS_CURVE_BW6_761) return group == SS_G1 ? &msm_ops_bw6_g1() : group == SS_G2 ? &msm_ops_bw6_g2() : nullptr;
+    return nullptr;
+}
+
+struct RatioJob {
+    int curve, group;
+    const uint8_t* v1;       // n elements (host, or device when host == false)
+    const uint8_t* v2;       // second vector for merge_pairs, or nullptr for power_pairs on v1
+    int compressed;
+    int check;               // CheckForCorrectness used when decoding
+    uint64_t n;              // elements in v1
+    int subgroup;            // 1: p.mul_bigint(r).is_zero() for every element of v1
+    int do_ratio;            // 1: produce (s, sx)
+    const uint8_t* rho;      // explicit scalars (HOST memory, one per pair) or nullptr
+    const uint8_t* seed;     // 32-byte ChaCha20 key (HOST memory) when rho == nullptr
+    uint8_t* out;            // re-encoded v1 (same memory kind as v1) or nullptr
+    int out_compressed;
+    uint8_t* out_s;          // HOST: uncompressed s, sx
+    uint8_t* out_sx;
+    const char* what;
+};
+
+int pick_window_bits(uint64_t pairs_per_tile) {
+    int lg = 0;
+    while ((1ull << (lg + 1)) <= pairs_per_tile) lg++;
+    int c = lg - 5;
+    if (c < 2) c = 2;
+    if (c > 13) c = 13;
+    return c;
+}
+
+int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user_stream) {
+    const GroupOps* op = group_ops(j.curve, j.group);
+    const MsmOps* mo = msm_ops(j.curve, j.group);
+    if (!op || !mo) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group %d/%d", j.curve, j.group);
+    const GroupOps& o = *op;
+    if (j.n == 0) return SS_OK;
+    const bool two = j.v2 != nullptr;
+    const uint64_t pairs = j.do_ratio ? (two ? j.n : j.n - 1) : 0;
+    if (j.do_ratio && pairs == 0) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: ratio check needs at least 2 elements", j.what);
+    const size_t isz = j.compressed ? o.csize : o.usize, osz = j.out_compressed ? o.csize : o.usize;
+    const size_t T = std::min<uint64_t>(tile_elems(), j.n);
+    const size_t ntiles = (j.n + T - 1) / T;
+    const int nbits = j.rho ? (j.curve == SS_CURVE_BLS12_377 ? 253 : 377) : 128;
+    const int c = pick_window_bits(std::min<uint64_t>(T, std::max<uint64_t>(pairs, 1)));
+    const int W = (nbits + c - 1) / c;
+    const uint32_t B = 1u << c;
+    const uint32_t seglen = B >= 256 ? B / 256 : 1, nseg = B / seglen;
+    const size_t fw = o.coord_words;
+
+    // slab layout
+    size_t need = 256 + align_up(ntiles * 16, 256);
+    const size_t aff_b = align_up((size_t)2 * fw * 4 * (T + 1), 256), inf_b = align_up(T + 1, 256);
+    need += (two ? 2 : 1) * (aff_b + inf_b);
+    if (host) need += (two ? 2 : 1) * align_up(isz * (T + 1), 256) + (j.out ? align_up(osz * T, 256) : 0);
+    size_t sort_b = 0, bucket_b = 0;
+    if (j.do_ratio) {
+        sort_b = 3 * align_up((size_t)W * B * 4, 256) + align_up((size_t)W * T * 4, 256) + (j.rho ? align_up((size_t)o.fr_bytes * T, 256) : 0);
+        bucket_b = align_up((size_t)3 * fw * 4 * 2 * W * B, 256) + align_up((size_t)3 * fw * 4 * 2 * W * nseg, 256) +
+                   align_up((size_t)3 * fw * 4 * 2 * W, 256) + 2 * align_up(o.usize, 256);
+    }
+    need += sort_b + bucket_b;
+    LaneGuard lg;
+    int rc = lane_acquire(device, need, &lg.l);
+    if (rc) return rc;
+    cudaStream_t s = (!host && user_stream) ? user_stream : lg.l->stream;
+    Carver cv(lg.l->buf);
+    unsigned long long* d_status = cv.take<unsigned long long>(ntiles * 16);
+    uint32_t* aff1 = cv.take<uint32_t>((size_t)2 * fw * 4 * (T + 1));
+    uint8_t* inf1 = cv.take<uint8_t>(T + 1);
+    uint32_t* aff2 = nullptr;
+    uint8_t* inf2 = nullptr;
+    if (two) {
+        aff2 = cv.take<uint32_t>((size_t)2 * fw * 4 * (T + 1));
+        inf2 = cv.take<uint8_t>(T + 1);
+    }
+    uint8_t *bi1 = nullptr, *bi2 = nullptr, *bo = nullptr;
+    if (host) {
+        bi1 = cv.take<uint8_t>(isz * (T + 1));
+        if (two) bi2 = cv.take<uint8_t>(isz * (T + 1));
+        if (j.out) bo = cv.take<uint8_t>(osz * T);
+    }
+    uint32_t *hist = nullptr, *cursor = nullptr, *counts = nullptr, *idx = nullptr, *buckets = nullptr, *segres = nullptr,
+             *winres = nullptr, *d_s = nullptr, *d_sx = nullptr;
+    uint8_t* d_rho = nullptr;
+    if (j.do_ratio) {
+        hist = cv.take<uint32_t>((size_t)W * B * 4);
+        cursor = cv.take<uint32_t>((size_t)W * B * 4);
+        counts = cv.take<uint32_t>((size_t)W * B * 4);
+        idx = cv.take<uint32_t>((size_t)W * T * 4);
+        if (j.rho) d_rho = cv.take<uint8_t>((size_t)o.fr_bytes * T);
+        buckets = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W * B);
+        segres = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W * nseg);
+        winres = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W);
+        d_s = cv.take<uint32_t>(o.usize);
+        d_sx = cv.take<uint32_t>(o.usize);
+        ProfScope ps("k_jac_fill_identity", o.name, (uint64_t)2 * W * B, s);
+        mo->fill_identity(buckets, (uint64_t)2 * W * B, s);
+    }
+    CU(cudaMemsetAsync(d_status, 0xff, ntiles * 16, s));
+
+    for (size_t t = 0; t < ntiles; t++) {
+        const uint64_t e0 = t * T;
+        const uint64_t own = std::min<uint64_t>(T, j.n - e0);                  // elements this tile owns
+        const uint64_t ne = two ? own : std::min<uint64_t>(T + 1, j.n - e0);   // decoded (one overlap for power_pairs)
+        const uint64_t np = j.do_ratio ? (two ? own : (e0 < pairs ? std::min<uint64_t>(T, pairs - e0) : 0)) : 0;
+        const uint64_t stride = ne;
+        const uint8_t* in1 = j.v1 + e0 * isz;
+        if (host) {
+            CU(cudaMemcpyAsync(bi1, in1, ne * isz, cudaMemcpyHostToDevice, s));
+            in1 = bi1;
+        }
+        {
+            DecodeArgs da = {reinterpret_cast<const uint32_t*>(in1), j.compressed, j.check, ne, aff1, inf1, d_status + 2 * t};
+            ProfScope ps("k_decode", o.name, ne, s);
+            o.decode(da, s);
+        }
+        if (two) {
+            const uint8_t* in2 = j.v2 + e0 * isz;
+            if (host) {
+                CU(cudaMemcpyAsync(bi2, in2, ne * isz, cudaMemcpyHostToDevice, s));
+                in2 = bi2;
+            }
+            DecodeArgs da = {reinterpret_cast<const uint32_t*>(in2), j.compressed, j.check, ne, aff2, inf2, d_status + 2 * t};
+            ProfScope ps("k_decode", o.name, ne, s);
+            o.decode(da, s);
+        }
+        if (j.subgroup) {
+            // only the first `own` elements: the overlap element belongs to the next tile.  The SoA
+            // stride is `ne`, so pass n = own through a strided view: k_subgroup indexes [i] with stride n,
+            // hence it is launched over `ne` with the count check inside the kernel args.
+            SubgroupArgs sa = {aff1, inf1, stride, d_status + 2 * t + 1, own};
+            ProfScope ps("k_subgroup", o.name, own, s);
+            o.subgroup(sa, s);
+        }
+        if (np) {
+            MsmSortArgs sa;
+            sa.rho.explicit_rho = nullptr;
+            if (j.rho) {
+                CU(cudaMemcpyAsync(d_rho, j.rho + e0 * o.fr_bytes, np * o.fr_bytes, cudaMemcpyHostToDevice, s));
+                sa.rho.explicit_rho = reinterpret_cast<const uint32_t*>(d_rho);
+            } else {
+                memcpy(sa.rho.key, j.seed, 32);
+            }
+            sa.rho.first_index = e0;
+            sa.rho.frw = o.fr_words;
+            sa.rho.nbits = nbits;
+            sa.n = np;
+            sa.c = c;
+            sa.W = W;
+            sa.hist = hist;
+            sa.cursor = cursor;
+            sa.idx = idx;
+            {
+                ProfScope ps("k_msm_sort", o.name, np, s);
+                msm_sort(sa, counts, s);
+            }
+            MsmAccArgs aa;
+            aa.aff1 = aff1;
+            aa.inf1 = inf1;
+            aa.aff2 = two ? aff2 : aff1 + 1;  // power_pairs: v2_i = v1_{i+1} (same SoA stride)
+            aa.inf2 = two ? inf2 : inf1 + 1;
+            aa.stride = stride;
+            aa.n = np;
+            aa.c = c;
+            aa.W = W;
+            aa.offsets = hist;
+            aa.counts = counts;
+            aa.idx = idx;
+            aa.buckets = buckets;
+            ProfScope ps("k_msm_accumulate", o.name, np, s);
+            mo->accumulate(aa, s);
+        }
+        if (j.out) {
+            uint8_t* dst = host ? bo : j.out + e0 * osz;
+            EncodeArgs ea = {aff1, inf1, stride, reinterpret_cast<uint32_t*>(dst), j.out_compressed, own};
+            {
+                ProfScope ps("k_encode", o.name, own, s);
+                o.encode(ea, s);
+            }
+            if (host) CU(cudaMemcpyAsync(j.out + e0 * osz, bo, own * osz, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (j.do_ratio) {
+        MsmReduceArgs ra = {buckets, c, W, seglen, nseg, segres, winres, d_s, d_sx};
+        {
+            ProfScope ps("k_msm_reduce", o.name, (uint64_t)2 * W * B, s);
+            mo->reduce(ra, s);
+        }
+        CU(cudaMemcpyAsync(j.out_s, d_s, o.usize, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(j.out_sx, d_sx, o.usize, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaGetLastError());
+    std::vector<unsigned long long> st(ntiles * 2);
+    CU(cudaMemcpyAsync(st.data(), d_status, ntiles * 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    prof_flush();
+    for (size_t t = 0; t < ntiles; t++) {
+        if ((rc = decode_status(st[2 * t], t * T, j.what))) return rc;
+        if ((rc = decode_status(st[2 * t + 1], t * T, j.what))) return rc;
+    }
+    return SS_OK;
+}
+
+int ratio_common_checks(int curve, int group, const void* v, size_t n, int check) {
+    if (!group_ops(curve, group)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group %d/%d", curve, group);
+    if (n && !v) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null input");
+    if (check < 0 || check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode %d", check);
+    return SS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ss_merge_pairs(int curve, int group, const uint8_t* v1, const uint8_t* v2, int compressed, int check, size_t n,
+                   const uint8_t* rho, const uint8_t* rho_seed, uint8_t* out_s, uint8_t* out_sx) {
+    int rc = ratio_common_checks(curve, group, v1, n, check);
+    if (rc) return rc;
+    if (!v2 || !out_s || !out_sx || (!rho && !rho_seed)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (n == 0) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "merge_pairs of empty vectors");
+    if ((rc = ensure_init())) return rc;
+    RatioJob j = {curve, group, v1, v2, compressed, check, n, 0, 1, rho, rho_seed, nullptr, 0, out_s, out_sx, "merge_pairs"};
+    return run_ratio_vector(g_devices[0], j, true, nullptr);
+}
+
+int ss_power_pairs(int curve, int group, const uint8_t* v, int compressed, int check, size_t n, const uint8_t* rho,
+                   const uint8_t* rho_seed, uint8_t* out_s, uint8_t* out_sx) {
+    int rc = ratio_common_checks(curve, group, v, n, check);
+    if (rc) return rc;
+    if (!out_s || !out_sx || (!rho && !rho_seed)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (n < 2) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "power_pairs needs at least 2 elements");
+    if ((rc = ensure_init())) return rc;
+    RatioJob j = {curve, group, v, nullptr, compressed, check, n, 0, 1, rho, rho_seed, nullptr, 0, out_s, out_sx, "power_pairs"};
+    return run_ratio_vector(g_devices[0], j, true, nullptr);
+}
+
+int ss_check_and_ratio(int curve, int group, const uint8_t* in, int in_compressed, size_t n, int subgroup_mode,
+                       int do_ratio, const uint8_t* rho, const uint8_t* rho_seed, uint8_t* out, int out_compressed,
+                       uint8_t* out_s, uint8_t* out_sx) {
+    int rc = ratio_common_checks(curve, group, in, n, SS_CHECK_ONLY_NON_ZERO);
+    if (rc) return rc;
+    if (subgroup_mode < 0 || subgroup_mode > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad subgroup mode");
+    if (do_ratio && (!out_s || !out_sx || (!rho && !rho_seed))) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (do_ratio && n < 2) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "ratio check needs at least 2 elements");
+    if (n == 0) return SS_OK;
+    if ((rc = ensure_init())) return rc;
+    RatioJob j = {curve, group, in, nullptr, in_compressed, SS_CHECK_ONLY_NON_ZERO, n, subgroup_mode != SS_SUBGROUP_NO,
+                  do_ratio, rho, rho_seed, out, out_compressed, out_s, out_sx, "check_and_ratio"};
+    return run_ratio_vector(g_devices[0], j, true, nullptr);
+}
+
+// Per-vector hot loop of Phase1::verification (phase1/src/verification.rs:217-411, Groth16) over the
+// whole response: for tau_g1, tau_g2, alpha_g1, beta_g1 -> nonzero + subgroup check, (s, sx) for the
+// caller's check_same_ratio, and the re-encoded vector written into new_challenge; beta_g2 is re-encoded
+// too (verification.rs:199-201).  `pairs` receives 4 x (s || sx) uncompressed in that vector order
+// (G1: 2*g1_usize, G2: 2*g2_usize bytes each).  PoK / generator / before-after checks on the first
+// elements (verification.rs:83-213) are O(1) pairing work and stay with the caller.
+static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
+                                    int compressed_output, uint8_t* new_challenge, size_t new_challenge_len,
+                                    int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                    const uint8_t* rho_seed, uint8_t* pairs, bool host, cudaStream_t stream) {
+    if (!p || !output) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (p->proving_system != SS_GROTH16) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "only Groth16 layout is implemented");
+    if (ratio_check && (!rho_seed || !pairs)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "ratio check needs rho_seed and pairs");
+    ss_phase1_sizes z;
+    int rc = phase1_sizes(p, &z);
+    if (rc) return rc;
+    const GroupOps& g1 = *group_ops(p->curve, SS_G1);
+    const GroupOps& g2 = *group_ops(p->curve, SS_G2);
+    const uint64_t need_out = compressed_output ? z.contribution_size - z.public_key_size : z.accumulator_size;
+    const uint64_t need_nc = compressed_new_challenge ? z.contribution_size - z.public_key_size : z.accumulator_size;
+    if (output_len < need_out) return fail(SS_ERR_INVALID_LENGTH, 0, need_out, output_len, "response buffer too short");
+    if (new_challenge && new_challenge_len < need_nc) return fail(SS_ERR_INVALID_LENGTH, 0, need_nc, new_challenge_len, "new_challenge buffer too short");
+    if ((rc = ensure_init())) return rc;
+    auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
+    const uint64_t n1 = z.g1_chunk_size, n2 = z.other_chunk_size;
+    const uint64_t cnt[5] = {n1, n2, n2, n2, 1};
+    const GroupOps* gs[5] = {&g1, &g2, &g1, &g1, &g2};
+    const int grp[5] = {SS_G1, SS_G2, SS_G1, SS_G1, SS_G2};
+    const char* names[5] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1", "beta_g2"};
+    uint64_t a = 64, b = 64, po = 0;
+    for (int v = 0; v < 5; v++) {
+        uint8_t* out = new_challenge ? new_challenge + b : nullptr;
+        if (cnt[v]) {
+            if (v < 4) {
+                // a vector of one element cannot be ratio-checked (verification.rs:238-241 -> BatchTooSmall)
+                if (ratio_check && cnt[v] < 2) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: batch too small", names[v]);
+                RatioJob j = {p->curve, grp[v], output + a, nullptr, compressed_output, SS_CHECK_ONLY_NON_ZERO, cnt[v],
+                              subgroup_mode != SS_SUBGROUP_NO, ratio_check, nullptr, rho_seed, out, compressed_new_challenge,
+                              pairs ? pairs + po : nullptr, pairs ? pairs + po + gs[v]->usize : nullptr, names[v]};
+                if ((rc = run_ratio_vector(g_devices[0], j, host, stream))) return rc;
+            } else if (out) {
+                // beta_g2: read with check_output_for_correctness (Full by default) and re-emit
+                RatioJob j = {p->curve, grp[v], output + a, nullptr, compressed_output, SS_CHECK_FULL, 1, 0, 0, nullptr, nullptr,
+                              out, compressed_new_challenge, nullptr, nullptr, names[v]};
+                if ((rc = run_ratio_vector(g_devices[0], j, host, stream))) return rc;
+            }
+        }
+        po += 2 * (uint64_t)gs[v]->usize;
+        a += cnt[v] * sz(*gs[v], compressed_output);
+        b += cnt[v] * sz(*gs[v], compressed_new_challenge);
+    }
+    return SS_OK;
+}
+
+int ss_phase1_verification_vectors(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
+                                   int compressed_output, uint8_t* new_challenge, size_t new_challenge_len,
+                                   int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                   const uint8_t* rho_seed, uint8_t* pairs) {
+    return phase1_verification_impl(p, output, output_len, compressed_output, new_challenge, new_challenge_len,
+                                    compressed_new_challenge, subgroup_mode, ratio_check, rho_seed, pairs, true, nullptr);
+}
+
+int ss_phase1_verification_vectors_dev(const ss_phase1_params* p, const void* d_output, size_t output_len,
+                                       int compressed_output, void* d_new_challenge, size_t new_challenge_len,
+                                       int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                       const uint8_t* rho_seed, uint8_t* pairs, void* stream) {
+    return phase1_verification_impl(p, static_cast<const uint8_t*>(d_output), output_len, compressed_output,
+                                    static_cast<uint8_t*>(d_new_challenge), new_challenge_len, compressed_new_challenge,
+                                    subgroup_mode, ratio_check, rho_seed, pairs, false, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,9 +1,13 @@
 // Kernel instantiations for Bw6G1 (one translation unit per group keeps nvcc compile times parallel).
-#include "kernels.cuh"
+#include "msm.cuh"
 
 namespace ss {
 const GroupOps& ops_bw6_g1() {
     static const GroupOps o = GroupLaunch<Bw6G1>::ops();
+    return o;
+}
+const MsmOps& msm_ops_bw6_g1() {
+    static const MsmOps o = MsmLaunch<Bw6G1>::ops();
     return o;
 }
 }  // namespace ss

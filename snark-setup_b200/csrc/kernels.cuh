@@ -258,15 +258,16 @@ __global__ void __launch_bounds__(128) k_normalize_encode(NormalizeArgs a) {
 struct EncodeArgs {
     const uint32_t* aff;
     const uint8_t* inf;
-    uint64_t n;
+    uint64_t n;  // SoA stride of `aff`
     uint32_t* out;
     int out_compressed;
+    uint64_t count;  // elements to encode (<= n)
 };
 
 template <class G>
 __global__ void __launch_bounds__(128) k_encode(EncodeArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= a.count) return;
     const int ow = (a.out_compressed ? G::CSIZE : G::USIZE) / 4;
     Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
     encode_point<G>(a.out + i * ow, a.out_compressed != 0, p);
@@ -276,14 +277,15 @@ __global__ void __launch_bounds__(128) k_encode(EncodeArgs a) {
 struct SubgroupArgs {
     const uint32_t* aff;
     const uint8_t* inf;
-    uint64_t n;
+    uint64_t n;  // SoA stride of `aff`
     unsigned long long* status;
+    uint64_t count;  // elements to check (<= n)
 };
 
 template <class G>
 __global__ void __launch_bounds__(128) k_subgroup(SubgroupArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= a.count) return;
     Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
     if (!in_subgroup_rmul<G>(p)) report(a.status, i, ERR_INCORRECT_SUBGROUP);
 }
@@ -329,12 +331,12 @@ struct GroupLaunch {
         k_decode<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
     }
     static void encode(const EncodeArgs& a, cudaStream_t s) {
-        if (!a.n) return;
-        k_encode<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+        if (!a.count) return;
+        k_encode<G><<<(unsigned)((a.count + 127) / 128), 128, 0, s>>>(a);
     }
     static void subgroup(const SubgroupArgs& a, cudaStream_t s) {
-        if (!a.n) return;
-        k_subgroup<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+        if (!a.count) return;
+        k_subgroup<G><<<(unsigned)((a.count + 127) / 128), 128, 0, s>>>(a);
     }
     static GroupOps ops() {
         GroupOps o;

@@ -244,6 +244,117 @@ def check_subgroup(curve, group, inp, compressed, mode=SUBGROUP_AUTO):
     _check(lib().ss_check_subgroup(curve, group, pin, int(compressed), n, mode))
 
 
+def _rho_args(curve, rho, seed):
+    fb = scalar_size(curve)
+    prho = None
+    keep = None
+    if rho is not None:
+        keep = b"".join(int(r).to_bytes(fb, "little") for r in rho)
+        prho = C.cast(C.c_char_p(keep), C.c_void_p)
+    pseed = bytes(seed) if seed is not None else None
+    if pseed is not None and len(pseed) != 32:
+        raise InvalidArgument("rho_seed must be 32 bytes")
+    return prho, pseed, keep
+
+
+def merge_pairs(curve, group, v1, v2, compressed, rho=None, seed=None, check=CHECK_NO):
+    """setup-utils/src/helpers.rs:371-384 -> (s, sx) as uncompressed element bytes."""
+    sz = element_size(curve, group, compressed)
+    usz = element_size(curve, group, False)
+    n = len(v1) // sz
+    if len(v2) // sz != n:
+        raise InvalidLength("merge_pairs", 0, n, len(v2) // sz)
+    s, sx = C.create_string_buffer(usz), C.create_string_buffer(usz)
+    p1, k1 = _buf(v1)
+    p2, k2 = _buf(v2)
+    prho, pseed, k3 = _rho_args(curve, rho, seed)
+    f = lib().ss_merge_pairs
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_char_p,
+                  C.c_void_p, C.c_void_p]
+    _check(f(curve, group, p1, p2, int(compressed), check, n, prho, pseed, s, sx))
+    return s.raw, sx.raw
+
+
+def power_pairs(curve, group, v, compressed, rho=None, seed=None, check=CHECK_NO):
+    """setup-utils/src/helpers.rs:388-390."""
+    sz = element_size(curve, group, compressed)
+    usz = element_size(curve, group, False)
+    n = len(v) // sz
+    s, sx = C.create_string_buffer(usz), C.create_string_buffer(usz)
+    p1, k1 = _buf(v)
+    prho, pseed, k3 = _rho_args(curve, rho, seed)
+    f = lib().ss_power_pairs
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_char_p, C.c_void_p,
+                  C.c_void_p]
+    _check(f(curve, group, p1, int(compressed), check, n, prho, pseed, s, sx))
+    return s.raw, sx.raw
+
+
+def check_and_ratio(curve, group, inp, in_compressed, subgroup_mode=SUBGROUP_AUTO, do_ratio=True, rho=None, seed=None,
+                    out_compressed=None):
+    """accumulator.rs:95-145 + :56-91 + the re-emit of verification.rs:271-274 -> (out bytes | None, s, sx)."""
+    sz = element_size(curve, group, in_compressed)
+    usz = element_size(curve, group, False)
+    n = len(inp) // sz
+    s, sx = C.create_string_buffer(usz), C.create_string_buffer(usz)
+    out = None
+    pout = None
+    if out_compressed is not None:
+        out = bytearray(n * element_size(curve, group, out_compressed))
+        pout, k0 = _buf(out) if n else (None, None)
+    p1, k1 = _buf(inp) if n else (None, None)
+    prho, pseed, k3 = _rho_args(curve, rho, seed)
+    f = lib().ss_check_and_ratio
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_char_p,
+                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    _check(f(curve, group, p1, int(in_compressed), n, subgroup_mode, int(do_ratio), prho, pseed, pout,
+             int(bool(out_compressed)), s, sx))
+    return (bytes(out) if out is not None else None), s.raw, sx.raw
+
+
+def phase1_verification_vectors(params, output, compressed_output, new_challenge, compressed_new_challenge,
+                                subgroup_mode=SUBGROUP_AUTO, ratio_check=True, seed=None):
+    """Hot loop of Phase1::verification (phase1/src/verification.rs:217-411).  `new_challenge` is a
+    bytearray written in place (or None).  Returns [(s, sx)] for tau_g1, tau_g2, alpha_g1, beta_g1."""
+    cv = params.curve
+    u1, u2 = element_size(cv, G1, False), element_size(cv, G2, False)
+    pairs = C.create_string_buffer(2 * (3 * u1 + u2))
+    pin, k1 = _buf(output)
+    pnc, k2 = _buf(new_challenge) if new_challenge is not None else (None, None)
+    f = lib().ss_phase1_verification_vectors
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                  C.c_char_p, C.c_void_p]
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                  C.c_int, C.c_char_p, C.c_void_p]
+    _check(f(C.byref(params.c), pin, len(output), int(compressed_output), pnc,
+             len(new_challenge) if new_challenge is not None else 0, int(compressed_new_challenge), subgroup_mode,
+             int(ratio_check), bytes(seed) if seed is not None else None, pairs))
+    out, o = [], 0
+    for usz in (u1, u2, u1, u1):
+        out.append((pairs.raw[o:o + usz], pairs.raw[o + usz:o + 2 * usz]))
+        o += 2 * usz
+    return out
+
+
+def phase1_verification_vectors_dev(params, d_output, output_len, compressed_output, d_new_challenge, nc_len,
+                                    compressed_new_challenge, subgroup_mode=SUBGROUP_AUTO, ratio_check=True, seed=None,
+                                    stream=0):
+    cv = params.curve
+    u1, u2 = element_size(cv, G1, False), element_size(cv, G2, False)
+    pairs = C.create_string_buffer(2 * (3 * u1 + u2))
+    f = lib().ss_phase1_verification_vectors_dev
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                  C.c_int, C.c_char_p, C.c_void_p, C.c_void_p]
+    _check(f(C.byref(params.c), d_output, output_len, int(compressed_output), d_new_challenge, nc_len,
+             int(compressed_new_challenge), subgroup_mode, int(ratio_check), bytes(seed) if seed is not None else None,
+             pairs, stream))
+    out, o = [], 0
+    for usz in (u1, u2, u1, u1):
+        out.append((pairs.raw[o:o + usz], pairs.raw[o + usz:o + 2 * usz]))
+        o += 2 * usz
+    return out
+
+
 class Phase1Parameters:
     """phase1/src/objects/parameters.rs:115-294."""
 
