@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "codec.cuh"
+#include "glv.cuh"
 
 namespace ss {
 
@@ -194,7 +195,11 @@ __global__ void __launch_bounds__(128) k_scalar_mul(ScalarMulArgs a) {
         }
         s = fp_from_mont(s);
     }
-    Jac<F> r = jac_mul_bits<F>(base, [&](int k) { return s.l[k]; }, FrP::BITS);
+#if defined(SS_SCALAR_MUL_LADDER)
+    Jac<F> r = jac_mul_bits<F>(base, [&](int k) { return s.l[k]; }, FrP::BITS);  // reference algorithm (A/B)
+#else
+    Jac<F> r = scalar_mul_endo<G>(base, s.l);  // GLV / GLS + signed windows + common-Z table (glv.cuh)
+#endif
     uint32_t* o = a.jac + i;
     FW::store(o, a.n, r.X);
     FW::store(o + (uint64_t)FW::W * a.n, a.n, r.Y);

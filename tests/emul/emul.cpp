@@ -3,6 +3,7 @@
 // Never linked into the product library.
 #include <cstring>
 #include "../../snark-setup_b200/csrc/codec.cuh"
+#include "../../snark-setup_b200/csrc/glv.cuh"
 
 using namespace ss;
 
@@ -128,7 +129,42 @@ static int point_add(const uint8_t* pa, const uint8_t* pb, int which, uint8_t* o
     return 0;
 }
 
+// k*P through the endomorphism path (glv.cuh), uncompressed in/out, scalar = canonical LE bytes
+template <class G>
+static int point_mul_endo(const uint8_t* in, const uint8_t* scalar, uint8_t* out) {
+    using F = typename G::F;
+    Affine<F> p;
+    uint32_t w[64];
+    memcpy(w, in, G::USIZE);
+    int e = decode_point<G>(w, false, CHECK_NO, p);
+    if (e) return e;
+    uint32_t k[12] = {0};
+    memcpy(k, scalar, 4 * G::Fr::N);
+    Jac<F> r = scalar_mul_endo<G>(p, k);
+    Affine<F> a;
+    if (r.is_identity()) {
+        a.inf = true;
+        a.x = F::zero();
+        a.y = F::zero();
+    } else {
+        a = jac_to_affine_with_zinv(r, fp_inv(r.Z));
+    }
+    uint32_t o[64];
+    encode_point<G>(o, false, a);
+    memcpy(out, o, G::USIZE);
+    return 0;
+}
+
 extern "C" {
+int emul_point_mul_endo(int group, const uint8_t* in, const uint8_t* scalar, uint8_t* out) {
+    switch (group) {
+        case 0: return point_mul_endo<Bls377G1>(in, scalar, out);
+        case 1: return point_mul_endo<Bls377G2>(in, scalar, out);
+        case 2: return point_mul_endo<Bw6G1>(in, scalar, out);
+        case 3: return point_mul_endo<Bw6G2>(in, scalar, out);
+    }
+    return -1;
+}
 // field: 0 Bls377Fq, 1 Bls377Fr, 2 Bw6Fq, 3 Bls377Fq2
 int emul_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     switch (field) {
