@@ -184,11 +184,19 @@ int lane_acquire(int device, size_t bytes, Lane** out) {
     Lane* ln = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        for (Lane* l : g_lanes)
-            if (!l->busy && l->device == device) {
-                ln = l;
-                break;
-            }
+        // best fit: the smallest free slab that is large enough, else the largest free one (to grow);
+        // keeps a 4 KB request from pinning a multi-GB slab and forcing other lanes to re-grow
+        Lane* fit = nullptr;
+        Lane* big = nullptr;
+        for (Lane* l : g_lanes) {
+            if (l->busy || l->device != device) continue;
+            if (l->cap >= bytes && (!fit || l->cap < fit->cap)) fit = l;
+            if (!big || l->cap > big->cap) big = l;
+        }
+        const size_t floor_b = std::max<size_t>(bytes, (size_t)1 << 20);
+        if (fit && fit->cap <= 64 * floor_b) ln = fit;
+        else if (!fit && big && bytes >= ((size_t)1 << 20)) ln = big;
+        // otherwise (tiny request, only huge slabs free): open a new small lane
         if (!ln) {
             ln = new Lane();
             ln->device = device;

@@ -12,6 +12,8 @@
 // which are the limbs themselves.
 #pragma once
 #include "ec.cuh"
+#include "glv.cuh"
+#include "sqrt_fast.cuh"
 
 namespace ss {
 
@@ -98,6 +100,83 @@ SS_HD bool in_subgroup_rmul(const Affine<typename G::F>& p) {
     return t.is_identity();
 }
 
+// ---- endomorphism subgroup tests for BLS12-377 -------------------------------------------------------
+// The reference tests membership with a full r-multiplication (elements.rs:138-142,
+// accumulator.rs:120-137).  For BLS12 curves the same predicate on curve points is
+//     G1:  phi'(P) == -[u^2] P  (and not uP == P)      Scott, eprint 2021/1130 §6
+//     G2:  psi(P)  ==  [u] P                             ibid. §4
+// which is what ark-bls12-377 0.4.0 itself ships as `is_in_correct_subgroup_assuming_on_curve`
+// (g1.rs / g2.rs).  u = 0x8508c00000000001 has 7 set bits: 63+6 group operations per [u] instead of
+// 253+87, identical for every lane.  tests/test_oracle_cpu.py checks verdict equality with the
+// r-multiplication on subgroup points, random curve points, pure cofactor torsion and mixed points.
+// BW6-761 keeps the r-multiplication (ark-bw6-761 0.4.0 has no fast test).  -DSS_SUBGROUP_RMUL forces
+// the reference algorithm everywhere.
+constexpr unsigned long long kBls377U = 0x8508c00000000001ull;
+
+template <class F>
+SS_HD Jac<F> jac_mul_u(const Affine<F>& p) {
+    Jac<F> acc{p.x, p.y, F::one()};
+#pragma unroll 1
+    for (int i = 62; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((kBls377U >> i) & 1) acc = jac_madd(acc, p);
+    }
+    return acc;
+}
+template <class F>
+SS_HD Jac<F> jac_mul_u(const Jac<F>& p) {
+    Jac<F> acc = p;
+#pragma unroll 1
+    for (int i = 62; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((kBls377U >> i) & 1) acc = jac_add(acc, p);
+    }
+    return acc;
+}
+// Jacobian J == affine A (both finite or both identity)
+template <class F>
+SS_HD bool jac_eq_affine(const Jac<F>& j, const F& ax, const F& ay) {
+    if (j.Z.is_zero()) return false;
+    F z2 = fp_sqr(j.Z);
+    if (!(j.X == fp_mul(ax, z2))) return false;
+    return j.Y == fp_mul(ay, fp_mul(z2, j.Z));
+}
+
+SS_HD bool in_subgroup_endo(const Affine<Fp<Bls377Fq>>& p, Bls377G1*) {
+    using F = Fp<Bls377Fq>;
+    if (p.inf) return true;
+    Jac<F> up = jac_mul_u<F>(p);
+    if (jac_eq_affine(up, p.x, p.y)) return false;  // uP == P, P != O
+    Jac<F> u2p = jac_mul_u<F>(up);
+    // phi'(x, y) = (beta' x, y) with beta' = beta^2 = -1 - beta;  -phi'(P) = (beta' x, -y)
+    F beta;
+#pragma unroll
+    for (int i = 0; i < 12; i++) beta.l[i] = Bls377G1Glv::beta(i);
+    F bx = fp_neg(fp_add(p.x, fp_mul(p.x, beta)));
+    return jac_eq_affine(u2p, bx, fp_neg(p.y));
+}
+SS_HD bool in_subgroup_endo(const Affine<Fp2<Bls377Fq>>& p, Bls377G2*) {
+    using F = Fp2<Bls377Fq>;
+    if (p.inf) return true;
+    Jac<F> up = jac_mul_u<F>(p);
+    F x = p.x, y = p.y;
+    Endo<Bls377G2>::apply(1, x, y);  // psi(P)
+    return jac_eq_affine(up, x, y);
+}
+template <class G>
+SS_HD bool in_subgroup_endo(const Affine<typename G::F>& p, G*) {
+    return in_subgroup_rmul<G>(p);
+}
+
+template <class G>
+SS_HD bool in_subgroup(const Affine<typename G::F>& p) {
+#if defined(SS_SUBGROUP_RMUL)
+    return in_subgroup_rmul<G>(p);
+#else
+    return in_subgroup_endo(p, (G*)nullptr);
+#endif
+}
+
 // Decode one element.  Returns ERR_*; `out` is valid when ERR_OK.
 template <class G>
 SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typename G::F>& out) {
@@ -113,7 +192,7 @@ SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typ
         } else {
             F rhs = fp_add(fp_mul(fp_sqr(out.x), out.x), G::b());
             F y;
-            if (!fp_sqrt(rhs, y)) return ERR_INVALID_DATA;
+            if (!fp_sqrt_any(rhs, y)) return ERR_INVALID_DATA;
             bool neg = IO::is_negative(IO::canonical(y));
             bool want_neg = (flags & FLAG_NEG_W) != 0;
             out.y = (neg == want_neg) ? y : fp_neg(y);
@@ -129,7 +208,7 @@ SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typ
         out.y = F::zero();
     } else if (check == CHECK_FULL || check == CHECK_ONLY_IN_GROUP) {
         if (!on_curve(out, G::b())) return ERR_INVALID_DATA;
-        if (!in_subgroup_rmul<G>(out)) return ERR_INVALID_DATA;
+        if (!in_subgroup<G>(out)) return ERR_INVALID_DATA;
     }
     if ((check == CHECK_FULL || check == CHECK_ONLY_NON_ZERO) && out.inf) return ERR_POINT_AT_INFINITY;
     return ERR_OK;

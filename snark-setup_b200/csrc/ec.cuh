@@ -108,9 +108,15 @@ using Bw6G1 = Bw6Group<Bw6G1Params>;
 using Bw6G2 = Bw6Group<Bw6G2Params>;
 
 // ---- formulas ---------------------------------------------------------------------------------
+// Group operations come in three flavours: *_inl (the formula), *_call (one out-of-line copy per
+// field, used for the wide fields where inlining every Fp2 / 24-limb add-sub chain makes the NVVM
+// front end take >10 minutes and kernels of hundreds of KB) and the dispatching jac_dbl / jac_madd /
+// jac_add.  jac_dbl_cold is the always-out-of-line doubling used by the exceptional P+P branches.
+template <class F>
+SS_HD Jac<F> jac_dbl_cold(const Jac<F>& p);
 // dbl-2009-l (a = 0): 2M + 5S
 template <class F>
-SS_HD Jac<F> jac_dbl(const Jac<F>& p) {
+SS_HD Jac<F> jac_dbl_inl(const Jac<F>& p) {
     if (p.Z.is_zero()) return p;
     F A = fp_sqr(p.X);
     F B = fp_sqr(p.Y);
@@ -129,7 +135,7 @@ SS_HD Jac<F> jac_dbl(const Jac<F>& p) {
 
 // madd-2007-bl: Jacobian + affine, 7M + 4S, with the exceptional cases handled
 template <class F>
-SS_HD Jac<F> jac_madd(const Jac<F>& p, const Affine<F>& q) {
+SS_HD Jac<F> jac_madd_inl(const Jac<F>& p, const Affine<F>& q) {
     if (q.inf) return p;
     if (p.Z.is_zero()) return Jac<F>{q.x, q.y, F::one()};
     F Z1Z1 = fp_sqr(p.Z);
@@ -138,7 +144,7 @@ SS_HD Jac<F> jac_madd(const Jac<F>& p, const Affine<F>& q) {
     F H = fp_sub(U2, p.X);
     F rr = fp_sub(S2, p.Y);
     if (H.is_zero()) {
-        if (rr.is_zero()) return jac_dbl(p);
+        if (rr.is_zero()) return jac_dbl_cold(p);
         return Jac<F>::identity();
     }
     rr = fp_dbl(rr);
@@ -155,7 +161,7 @@ SS_HD Jac<F> jac_madd(const Jac<F>& p, const Affine<F>& q) {
 
 // add-2007-bl: Jacobian + Jacobian, 11M + 5S
 template <class F>
-SS_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
+SS_HD Jac<F> jac_add_inl(const Jac<F>& p, const Jac<F>& q) {
     if (p.Z.is_zero()) return q;
     if (q.Z.is_zero()) return p;
     F Z1Z1 = fp_sqr(p.Z);
@@ -167,7 +173,7 @@ SS_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
     F H = fp_sub(U2, U1);
     F rr = fp_sub(S2, S1);
     if (H.is_zero()) {
-        if (rr.is_zero()) return jac_dbl(p);
+        if (rr.is_zero()) return jac_dbl_cold(p);
         return Jac<F>::identity();
     }
     rr = fp_dbl(rr);
@@ -179,6 +185,51 @@ SS_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
     r.Y = fp_sub(fp_mul(rr, fp_sub(V, r.X)), fp_dbl(fp_mul(S1, J)));
     r.Z = fp_mul(fp_sub(fp_sub(fp_sqr(fp_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
     return r;
+}
+
+#if defined(__CUDACC__)
+template <class F>
+__device__ __noinline__ Jac<F> jac_dbl_call(Jac<F> p) {
+    return jac_dbl_inl(p);
+}
+template <class F>
+__device__ __noinline__ Jac<F> jac_madd_call(Jac<F> p, Affine<F> q) {
+    return jac_madd_inl(p, q);
+}
+template <class F>
+__device__ __noinline__ Jac<F> jac_add_call(Jac<F> p, Jac<F> q) {
+    return jac_add_inl(p, q);
+}
+#endif
+
+template <class F>
+SS_HD Jac<F> jac_dbl_cold(const Jac<F>& p) {
+#if defined(__CUDA_ARCH__)
+    return jac_dbl_call<F>(p);
+#else
+    return jac_dbl_inl(p);
+#endif
+}
+template <class F>
+SS_HD Jac<F> jac_dbl(const Jac<F>& p) {
+#if defined(__CUDA_ARCH__) && !defined(SS_GROUP_INLINE)
+    if constexpr (F::CALL_GROUP_OPS) return jac_dbl_call<F>(p);
+#endif
+    return jac_dbl_inl(p);
+}
+template <class F>
+SS_HD Jac<F> jac_madd(const Jac<F>& p, const Affine<F>& q) {
+#if defined(__CUDA_ARCH__) && !defined(SS_GROUP_INLINE)
+    if constexpr (F::CALL_GROUP_OPS) return jac_madd_call<F>(p, q);
+#endif
+    return jac_madd_inl(p, q);
+}
+template <class F>
+SS_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
+#if defined(__CUDA_ARCH__) && !defined(SS_GROUP_INLINE)
+    if constexpr (F::CALL_GROUP_OPS) return jac_add_call<F>(p, q);
+#endif
+    return jac_add_inl(p, q);
 }
 
 template <class F>

@@ -19,6 +19,10 @@ template <class P>
 struct Fp {
     static constexpr int N = P::N;
     using Params = P;
+#ifndef SS_CALL_GROUP_OPS_LIMBS
+#define SS_CALL_GROUP_OPS_LIMBS 12  // group ops are out-of-line for fields wider than this
+#endif
+    static constexpr bool CALL_GROUP_OPS = (N > SS_CALL_GROUP_OPS_LIMBS);
     uint32_t l[N];
 
     SS_HD static Fp zero() {
@@ -209,9 +213,133 @@ SS_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #endif
 }
 
+// ---- dedicated squaring --------------------------------------------------------------------------
+// a^2 = 2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum_i a_i^2 2^(64 i): N(N+1)/2 wide products instead of N^2,
+// followed by a separate Montgomery reduction of the 2N-limb square (N^2 wide products): 222 instead
+// of 288 IMAD.WIDE for N = 12.  Off-diagonal products are accumulated in two 2N-limb arrays so that
+// every product again lands on an aligned register pair: E[k] sits at limb position k and takes the
+// products with even i+j, O[k] sits at position k+1 and takes the odd ones.  Rows are processed in
+// increasing i, so the limb after the end of each chain has only ever received carry bits and one
+// `addc` closes the chain.
+
+// reduction iteration with the >>32 folded into the odd chain (mont_step with a := p, b_i := m)
+template <class P>
+SS_HD void mont_redc_shift_step(uint32_t* X /*old Y*/, uint32_t* Y /*old X*/) {
+    constexpr int N = P::N;
+    uint32_t m = mul_lo(X[0] + Y[1], P::inv());
+    X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        Y[j] = madc_lo_cc(P::mod(j + 1), m, Y[j + 2]);
+        Y[j + 1] = madc_hi_cc(P::mod(j + 1), m, Y[j + 3]);
+    }
+    Y[N - 2] = madc_lo_cc(P::mod(N - 1), m, 0);
+    Y[N - 1] = madc_hi(P::mod(N - 1), m, 0);
+    X[0] = mad_lo_cc(P::mod(0), m, X[0]);
+    X[1] = madc_hi_cc(P::mod(0), m, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(P::mod(j), m, X[j]);
+        X[j + 1] = madc_hi_cc(P::mod(j), m, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0);
+}
+
+template <class P>
+SS_HD Fp<P> fp_sqr_inl(const Fp<P>& av) {
+    constexpr int N = P::N;
+    const uint32_t* a = av.l;
+    uint32_t E[2 * N], O[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) {
+        // odd i+j: j = i+1, i+3, ...  -> O[p-1], O[p]
+        {
+            int last = -1;
+#pragma unroll
+            for (int j = i + 1; j < N; j += 2) {
+                const int p = i + j;
+                O[p - 1] = (j == i + 1) ? mad_lo_cc(a[i], a[j], O[p - 1]) : madc_lo_cc(a[i], a[j], O[p - 1]);
+                O[p] = madc_hi_cc(a[i], a[j], O[p]);
+                last = p;
+            }
+            if (last >= 0) O[last + 1] = addc(O[last + 1], 0);
+        }
+        // even i+j: j = i+2, i+4, ... -> E[p], E[p+1]
+        {
+            int last = -1;
+#pragma unroll
+            for (int j = i + 2; j < N; j += 2) {
+                const int p = i + j;
+                E[p] = (j == i + 2) ? mad_lo_cc(a[i], a[j], E[p]) : madc_lo_cc(a[i], a[j], E[p]);
+                E[p + 1] = madc_hi_cc(a[i], a[j], E[p + 1]);
+                last = p;
+            }
+            if (last >= 0) E[last + 2] = addc(E[last + 2], 0);
+        }
+    }
+    // D = E + O * 2^32  (into E)
+    E[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * N - 1; k++) E[k] = addc_cc(E[k], O[k - 1]);
+    E[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+    // T = 2 D
+    E[0] = add_cc(E[0], E[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * N - 1; k++) E[k] = addc_cc(E[k], E[k]);
+    E[2 * N - 1] = addc(E[2 * N - 1], E[2 * N - 1]);
+    // T += sum a_i^2 2^(64 i)
+    E[0] = mad_lo_cc(a[0], a[0], E[0]);
+    E[1] = madc_hi_cc(a[0], a[0], E[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) {
+        E[2 * i] = madc_lo_cc(a[i], a[i], E[2 * i]);
+        E[2 * i + 1] = madc_hi_cc(a[i], a[i], E[2 * i + 1]);
+    }
+    E[2 * N - 2] = madc_lo_cc(a[N - 1], a[N - 1], E[2 * N - 2]);
+    E[2 * N - 1] = madc_hi(a[N - 1], a[N - 1], E[2 * N - 1]);
+    // Montgomery reduction of T_lo; X aligned at 0 = T[0..N), Y = 0
+    uint32_t* X = E;  // low half is consumed in place
+    uint32_t Y[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) Y[k] = 0;
+    mont_reduce_step<P>(X, Y);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_redc_shift_step<P>(Y, X);
+        if (i + 1 < N) mont_redc_shift_step<P>(X, Y);
+    }
+    // W = Yrole + (Xrole >> 32) with Xrole = Y, Yrole = X (odd number of swaps), then + T_hi
+    Fp<P> r;
+    r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(X[j], Y[j + 1]);
+    r.l[N - 1] = addc(X[N - 1], 0);
+    r.l[0] = add_cc(r.l[0], E[N]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(r.l[j], E[N + j]);
+    r.l[N - 1] = addc(r.l[N - 1], E[2 * N - 1]);
+    fp_final_sub<P>(r.l);
+    return r;
+}
+
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Fp<P> fp_sqr_call(Fp<P> a) {
+    return fp_sqr_inl(a);
+}
+#endif
+
 template <class P>
 SS_HD Fp<P> fp_sqr(const Fp<P>& a) {
+#if defined(SS_NO_DEDICATED_SQR)
     return fp_mul(a, a);
+#elif defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+    return fp_sqr_call<P>(a);
+#else
+    return fp_sqr_inl(a);
+#endif
 }
 
 // Montgomery form <-> canonical integer

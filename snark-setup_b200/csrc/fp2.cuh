@@ -9,6 +9,7 @@ template <class P>
 struct Fp2 {
     using Base = Fp<P>;
     using Params = P;
+    static constexpr bool CALL_GROUP_OPS = true;
     Base c0, c1;
 
     SS_HD static Fp2 zero() { return Fp2{Base::zero(), Base::zero()}; }

@@ -228,6 +228,15 @@ struct Endo<Bls377G2> {
     }
 };
 
+// out-of-line plain ladder for the (never taken on subgroup inputs) tiny-order fallback
+template <class G>
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#endif
+Jac<typename G::F> jac_mul_ladder_cold(Affine<typename G::F> base, const uint32_t* k) {
+    return jac_mul_bits<typename G::F>(base, [&](int i) { return k[i]; }, G::Fr::Params::BITS);
+}
+
 // ---- k * P ----------------------------------------------------------------------------------------
 // `k` canonical little-endian words (G::Fr::N of them), k < r.
 template <class G>
@@ -243,6 +252,7 @@ SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, cons
         tx[0] = t.X; ty[0] = t.Y; tz[0] = t.Z;
         t = jac_dbl(t);
         tx[1] = t.X; ty[1] = t.Y; tz[1] = t.Z;
+#pragma unroll 1
         for (int j = 2; j < TS; j++) {
             t = jac_madd(t, base);
             tx[j] = t.X; ty[j] = t.Y; tz[j] = t.Z;
@@ -255,7 +265,7 @@ SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, cons
     F zc = fp_mul(pre[TS - 1], tz[TS - 1]);
     if (zc.is_zero()) {
         // some j*P (j <= 8) is the identity: P has tiny order — take the plain ladder
-        return jac_mul_bits<F>(base, [&](int i) { return k[i]; }, G::Fr::Params::BITS);
+        return jac_mul_ladder_cold<G>(base, k);
     }
     F extra;
     const bool has_extra = E::real_factor(zc, extra);
@@ -279,11 +289,10 @@ SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, cons
     Jac<F> acc = Jac<F>::identity();
     for (int i = ND - 1; i >= 0; i--) {
         if (i != ND - 1) {
-            acc = jac_dbl(acc);
-            acc = jac_dbl(acc);
-            acc = jac_dbl(acc);
-            acc = jac_dbl(acc);
+#pragma unroll 1
+            for (int d = 0; d < 4; d++) acc = jac_dbl(acc);
         }
+#pragma unroll 1
         for (int j = 0; j < DIMS; j++) {
             int d = dig[j * ND + i];
             if (d != 0) {

@@ -165,9 +165,15 @@ struct ScalarMulArgs {
 };
 
 // bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
-// Jacobian form for k_normalize_encode.  v1: the reference's MSB-first double-and-add.
+// Jacobian form for k_normalize_encode.
+#ifndef SS_SMUL_TPB
+#define SS_SMUL_TPB 128
+#endif
+#ifndef SS_SMUL_MINB
+#define SS_SMUL_MINB 1
+#endif
 template <class G>
-__global__ void __launch_bounds__(128) k_scalar_mul(ScalarMulArgs a) {
+__global__ void __launch_bounds__(SS_SMUL_TPB, SS_SMUL_MINB) k_scalar_mul(ScalarMulArgs a) {
     using F = typename G::F;
     using FrP = typename G::Fr::Params;
     using FW = FieldWords<F>;
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(128) k_subgroup(SubgroupArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.count) return;
     Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
-    if (!in_subgroup_rmul<G>(p)) report(a.status, i, ERR_INCORRECT_SUBGROUP);
+    if (!in_subgroup<G>(p)) report(a.status, i, ERR_INCORRECT_SUBGROUP);
 }
 
 // ---- function table seen by api.cu -------------------------------------------------------------
@@ -325,7 +331,7 @@ struct GroupLaunch {
     }
     static void scalar_mul(const ScalarMulArgs& a, cudaStream_t s) {
         if (!a.n) return;
-        k_scalar_mul<G><<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+        k_scalar_mul<G><<<(unsigned)((a.n + SS_SMUL_TPB - 1) / SS_SMUL_TPB), SS_SMUL_TPB, 0, s>>>(a);
     }
     static void normalize_encode(const NormalizeArgs& a, cudaStream_t s) {
         if (!a.n) return;

@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-lib_path = os.path.join(_CSRC, "libsnarksetup_b200.so")
+lib_path = os.environ.get("SS_LIB") or os.path.join(_CSRC, "libsnarksetup_b200.so")  # SS_LIB: A/B kernel variants
 
 BLS12_377, BW6_761 = 0, 1
 G1, G2 = 0, 1

@@ -29,7 +29,7 @@ static int fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
         case 2: r = fp_sub(x, y); break;
         case 3: r = fp_neg(x); break;
         case 4: r = fp_inv(x); break;
-        case 5: rc = fp_sqrt(x, r) ? 0 : 1; if (rc) r = Fp<P>::zero(); break;
+        case 5: rc = fp_sqrt_any(x, r) ? 0 : 1; if (rc) r = Fp<P>::zero(); break;
         case 6: r = fp_sqr(x); break;
         default: return -1;
     }
@@ -49,7 +49,7 @@ static int fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
         case 2: r = fp_sub(x, y); break;
         case 3: r = fp_neg(x); break;
         case 4: r = fp_inv(x); break;
-        case 5: rc = fp_sqrt(x, r) ? 0 : 1; if (rc) r = Fp2<P>::zero(); break;
+        case 5: rc = fp_sqrt_any(x, r) ? 0 : 1; if (rc) r = Fp2<P>::zero(); break;
         case 6: r = fp_sqr(x); break;
         default: return -1;
     }
@@ -155,7 +155,28 @@ static int point_mul_endo(const uint8_t* in, const uint8_t* scalar, uint8_t* out
     return 0;
 }
 
+template <class G>
+static int subgroup_both(const uint8_t* in) {
+    using F = typename G::F;
+    Affine<F> p;
+    uint32_t w[64];
+    memcpy(w, in, G::USIZE);
+    int e = decode_point<G>(w, false, CHECK_NO, p);
+    if (e) return -e;
+    return (in_subgroup<G>(p) ? 1 : 0) | (in_subgroup_rmul<G>(p) ? 2 : 0);
+}
+
 extern "C" {
+// bit0: endomorphism test, bit1: r-multiplication
+int emul_in_subgroup(int group, const uint8_t* in) {
+    switch (group) {
+        case 0: return subgroup_both<Bls377G1>(in);
+        case 1: return subgroup_both<Bls377G2>(in);
+        case 2: return subgroup_both<Bw6G1>(in);
+        case 3: return subgroup_both<Bw6G2>(in);
+    }
+    return -100;
+}
 int emul_point_mul_endo(int group, const uint8_t* in, const uint8_t* scalar, uint8_t* out) {
     switch (group) {
         case 0: return point_mul_endo<Bls377G1>(in, scalar, out);

@@ -1,0 +1,116 @@
+"""Host-emulated build of the device ALGORITHMS that go beyond the reference's (glv.cuh, sqrt_fast.cuh,
+the endomorphism subgroup tests in codec.cuh, the dedicated squaring in fp.cuh) against pyref.
+Every one of them must give the same group element / verdict as the reference algorithm."""
+import ctypes
+import random
+
+import pytest
+
+import pyref as R
+from test_device_math_emul import L  # noqa: F401  (fixture: builds tests/emul/libemul.so)
+
+GROUPS = [R.BLS12_377.g1, R.BLS12_377.g2, R.BW6_761.g1, R.BW6_761.g2]
+U = 0x8508c00000000001
+
+
+def tb(v, n):
+    return v.to_bytes(n, "little")
+
+
+@pytest.mark.parametrize("gid", [0, 1, 2, 3])
+def test_endomorphism_scalar_mul(L, gid):
+    """GLV / GLS + signed windows + common-Z table == plain k*P, incl. edge scalars."""
+    g = GROUPS[gid]
+    rng = random.Random(90 + gid)
+    nb = (g.r.bit_length() + 7) // 8
+    ks = [0, 1, 2, 7, 8, 9, 15, 16, 17, g.r - 1, g.r - 2, U, U - 1, U + 1, U * U, U * U - 1, U ** 3, (1 << 127),
+          (1 << 128) - 1] + [rng.randrange(g.r) for _ in range(12)]
+    for k in ks:
+        k %= g.r
+        P = g.mul(g.gen, rng.randrange(1, g.r))
+        out = ctypes.create_string_buffer(g.usize)
+        assert L.emul_point_mul_endo(gid, g.encode(P, 0), tb(k, nb), out) == 0
+        assert out.raw == g.encode(g.mul(P, k), 0), (g.name, hex(k))
+    out = ctypes.create_string_buffer(g.usize)
+    assert L.emul_point_mul_endo(gid, g.encode(None, 0), tb(5, nb), out) == 0 and out.raw == g.encode(None, 0)
+
+
+def test_endomorphism_scalar_mul_tiny_order_points(L):
+    """2- and 3-torsion points make a table entry the identity: the out-of-line ladder takes over."""
+    g, q = R.BLS12_377.g1, R.BLS12_377_Q
+    for P in ((q - 1, 0), (0, 1), (0, q - 1)):
+        assert g.on_curve(P)
+        for k in (0, 1, 2, 3, 4, 5, 6, 12345678901234567890, g.r - 1):
+            out = ctypes.create_string_buffer(96)
+            assert L.emul_point_mul_endo(0, g.encode(P, 0), tb(k, 32), out) == 0
+            assert out.raw == g.encode(g.mul(P, k), 0), (P, k)
+
+
+@pytest.mark.parametrize("fid,p,nb", [(0, R.BLS12_377_Q, 48), (1, R.BLS12_377_R, 32), (2, R.BW6_761_Q, 96)])
+def test_dedicated_squaring_carry_patterns(L, fid, p, nb):
+    rng = random.Random(fid)
+    n32 = nb // 4
+    vals = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (1 << (p.bit_length() - 1)) - 1, 1 << (p.bit_length() - 1)]
+    vals += [((1 << (32 * k)) - 1) % p for k in range(1, n32)] + [(p - (1 << (32 * k))) % p for k in range(1, n32)]
+    for _ in range(200):
+        vals.append(int.from_bytes(b"".join(rng.choice([b"\xff" * 4, b"\x00" * 4, rng.randbytes(4)]) for _ in range(n32)),
+                                   "little") % p)
+    for a in vals:
+        out = ctypes.create_string_buffer(nb)
+        assert L.emul_field_op(fid, 6, tb(a, nb), tb(a, nb), out) == 0
+        assert out.raw == tb(a * a % p, nb), hex(a)
+
+
+def test_table_driven_sqrt(L):
+    q, nb = R.BLS12_377_Q, 48
+    F, f2 = R.Fp(q), R.BLS12_377.g2.F
+    rng = random.Random(12)
+    for it in range(120):
+        a = [0, 1, 4, q - 1, 5, q - 5, 2, 3][it] if it < 8 else (pow(rng.randrange(1, q), 2, q) if it % 2 else rng.randrange(q))
+        out = ctypes.create_string_buffer(nb)
+        rc = L.emul_field_op(0, 5, tb(a, nb), tb(a, nb), out)
+        if F.sqrt(a) is None:
+            assert rc == 1
+        else:
+            g = int.from_bytes(out.raw, "little")
+            assert rc == 0 and g * g % q == a
+    for it in range(120):
+        a = (rng.randrange(q), rng.randrange(q))
+        if it % 2 == 0:
+            a = f2.sqr(a)
+        a = {1: (rng.randrange(q), 0), 3: (5, 0), 5: (q - 5, 0), 7: (0, rng.randrange(q)), 9: (0, 0)}.get(it, a)
+        ab = tb(a[0], nb) + tb(a[1], nb)
+        out = ctypes.create_string_buffer(2 * nb)
+        rc = L.emul_field_op(3, 5, ab, ab, out)
+        if f2.sqrt(a) is None:
+            assert rc == 1
+        else:
+            g = (int.from_bytes(out.raw[:nb], "little"), int.from_bytes(out.raw[nb:], "little"))
+            assert rc == 0 and f2.sqr(g) == a
+
+
+@pytest.mark.parametrize("gid", [0, 1, 2, 3])
+def test_subgroup_test_equals_r_multiplication(L, gid):
+    """codec.cuh in_subgroup<G> (endomorphism test on BLS12-377) == p.mul_bigint(r).is_zero() on subgroup
+    points, random curve points, pure cofactor torsion, mixed points and small-order points."""
+    g = GROUPS[gid]
+    q = R.BLS12_377_Q
+    rng = random.Random(8 + gid)
+
+    def rnd():
+        while True:
+            x = rng.randrange(g.F.p) if g.F.degree == 1 else (rng.randrange(q), rng.randrange(q))
+            try:
+                return g.decode(g.F.to_bytes(x, 0, 2), True, R.NO)
+            except R.InvalidData:
+                pass
+
+    pts = [None] + [g.mul(g.gen, rng.randrange(1, g.r)) for _ in range(4)]
+    for _ in range(4):
+        Pn = rnd()
+        pts += [Pn, g.mul(Pn, g.r), g.add(g.mul(g.gen, rng.randrange(1, g.r)), g.mul(Pn, g.r))]
+    if gid == 0:
+        pts += [(q - 1, 0), (0, 1), (0, q - 1)]
+    for P in pts:
+        rc = L.emul_in_subgroup(gid, g.encode(P, 0))
+        assert rc == (3 if g.in_subgroup(P) else 0), (g.name, P, rc)

@@ -57,6 +57,37 @@ __global__ void k_imad_wide_x(uint32_t* out, int iters, uint32_t seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+__global__ void k_dfma(double* out, int iters, double seed) {
+    double a[8], b = seed, c = 1.0 / 3.0;
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(a[i], b, c);
+    }
+    double r = 0;
+    for (int i = 0; i < 8; i++) r += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// IMAD and DFMA issued from the same warp: do the two pipes overlap?
+__global__ void k_imad_dfma(double* out, int iters, double seed, uint32_t iseed) {
+    double a[4], b = seed, c = 1.0 / 3.0;
+    uint32_t x[8], y = iseed | 1, z = threadIdx.x;
+    for (int i = 0; i < 4; i++) a[i] = threadIdx.x + i;
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = fma(a[i], b, c);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = x[i] * y + z;
+    }
+    double r = 0;
+    for (int i = 0; i < 4; i++) r += a[i];
+    uint32_t q = 0;
+    for (int i = 0; i < 8; i++) q ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r + q;
+}
+
 template <class P>
 __global__ void k_fpmul(uint32_t* out, int iters, uint32_t seed) {
     Fp<P> x, y;
@@ -113,6 +144,14 @@ int main() {
         printf("{\"bench\": \"imad_wide\", \"threads_per_sm\": 2048, \"tpb\": %d, \"gops\": %.1f}\n", tpb, (double)blocks * tpb * iters * 8 / t * 1e-9);
         t = time_kernel([&] { k_imad_wide_x<<<blocks, tpb>>>(out, iters, 12345); }, 5);
         printf("{\"bench\": \"imad_wide_x_chain\", \"threads_per_sm\": 2048, \"tpb\": %d, \"gops\": %.1f}\n", tpb, (double)blocks * tpb * iters * 8 / t * 1e-9);
+    }
+    {
+        int tpb = 256, blocks = sms * 8;
+        double t = time_kernel([&] { k_dfma<<<blocks, tpb>>>((double*)out, iters, 1.0000001); }, 5);
+        printf("{\"bench\": \"dfma\", \"gops\": %.1f}\n", (double)blocks * tpb * iters * 8 / t * 1e-9);
+        t = time_kernel([&] { k_imad_dfma<<<blocks, tpb>>>((double*)out, iters, 1.0000001, 777); }, 5);
+        printf("{\"bench\": \"imad8+dfma4 per iter\", \"imad_gops\": %.1f, \"dfma_gops\": %.1f}\n",
+               (double)blocks * tpb * iters * 8 / t * 1e-9, (double)blocks * tpb * iters * 4 / t * 1e-9);
     }
     CK(cudaGetLastError());
 #ifdef SS_MUL_INLINE
