@@ -44,8 +44,19 @@ int pick_window_bits(uint64_t pairs_per_tile) {
     while ((1ull << (lg + 1)) <= pairs_per_tile) lg++;
     int c = lg - 5;
     if (c < 2) c = 2;
-    if (c > 13) c = 13;
+    if (c > 15) c = 15;
     return c;
+}
+
+size_t ratio_tile_elems() {
+    static size_t t = [] {
+        const char* e = getenv("SS_RATIO_TILE_LOG2");
+        int l = e ? atoi(e) : 20;
+        if (l < 8) l = 8;
+        if (l > 24) l = 24;
+        return (size_t)1 << l;
+    }();
+    return t;
 }
 
 int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user_stream) {
@@ -58,13 +69,26 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     const uint64_t pairs = j.do_ratio ? (two ? j.n : j.n - 1) : 0;
     if (j.do_ratio && pairs == 0) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: ratio check needs at least 2 elements", j.what);
     const size_t isz = j.compressed ? o.csize : o.usize, osz = j.out_compressed ? o.csize : o.usize;
-    const size_t T = std::min<uint64_t>(tile_elems(), j.n);
+    // ratio jobs use larger tiles than batch_exp: W*B bucket threads per tile must be several waves of the
+    // machine (2^20 pairs -> c = 15 -> 9 x 32768 buckets), see profiles/r01_ncu_msm_accumulate.md
+    const size_t T = std::min<uint64_t>(j.do_ratio ? ratio_tile_elems() : tile_elems(), j.n);
     const size_t ntiles = (j.n + T - 1) / T;
-    const int nbits = j.rho ? (j.curve == SS_CURVE_BLS12_377 ? 253 : 377) : 128;
-    const int c = pick_window_bits(std::min<uint64_t>(T, std::max<uint64_t>(pairs, 1)));
+    // Window width c and scalar width.  Every window must be FULL: a top window of b < c bits has only
+    // 2^b - 1 buckets holding n / 2^b points each, and one thread per bucket then serialises the whole
+    // tile (measured: 3.2 s instead of 9 ms at n = 2^19, c = 14, 128-bit rho).  Generated rho therefore
+    // gets W*c >= 128 bits (ChaCha20 supplies 512); for caller-supplied full-width scalars c is lowered
+    // until it (almost) divides the field size (253 = 23 * 11, 377 = 29 * 13).
+    int c = pick_window_bits(std::min<uint64_t>(T, std::max<uint64_t>(pairs, 1)));
+    int nbits;
+    if (!j.rho) {
+        nbits = ((128 + c - 1) / c) * c;
+    } else {
+        nbits = j.curve == SS_CURVE_BLS12_377 ? 253 : 377;
+        while (c > 2 && !(nbits % c == 0 || nbits % c >= c - 1)) c--;
+    }
     const int W = (nbits + c - 1) / c;
     const uint32_t B = 1u << c;
-    const uint32_t seglen = B >= 256 ? B / 256 : 1, nseg = B / seglen;
+    const uint32_t seglen = B >= 1024 ? 32 : (B >= 256 ? B / 256 : 1), nseg = B / seglen;
     const size_t fw = o.coord_words;
 
     // slab layout
@@ -74,7 +98,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     if (host) need += (two ? 2 : 1) * align_up(isz * (T + 1), 256) + (j.out ? align_up(osz * T, 256) : 0);
     size_t sort_b = 0, bucket_b = 0;
     if (j.do_ratio) {
-        sort_b = 3 * align_up((size_t)W * B * 4, 256) + align_up((size_t)W * T * 4, 256) + (j.rho ? align_up((size_t)o.fr_bytes * T, 256) : 0);
+        sort_b = 4 * align_up((size_t)W * B * 4, 256) + 1024 + align_up((size_t)W * T * 4, 256) + (j.rho ? align_up((size_t)o.fr_bytes * T, 256) : 0);
         bucket_b = align_up((size_t)3 * fw * 4 * 2 * W * B, 256) + align_up((size_t)3 * fw * 4 * 2 * W * nseg, 256) +
                    align_up((size_t)3 * fw * 4 * 2 * W, 256) + 2 * align_up(o.usize, 256);
     }
@@ -99,13 +123,15 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
         if (two) bi2 = cv.take<uint8_t>(isz * (T + 1));
         if (j.out) bo = cv.take<uint8_t>(osz * T);
     }
-    uint32_t *hist = nullptr, *cursor = nullptr, *counts = nullptr, *idx = nullptr, *buckets = nullptr, *segres = nullptr,
+    uint32_t *hist = nullptr, *cursor = nullptr, *counts = nullptr, *order = nullptr, *bins = nullptr, *idx = nullptr, *buckets = nullptr, *segres = nullptr,
              *winres = nullptr, *d_s = nullptr, *d_sx = nullptr;
     uint8_t* d_rho = nullptr;
     if (j.do_ratio) {
         hist = cv.take<uint32_t>((size_t)W * B * 4);
         cursor = cv.take<uint32_t>((size_t)W * B * 4);
         counts = cv.take<uint32_t>((size_t)W * B * 4);
+        order = cv.take<uint32_t>((size_t)W * B * 4);
+        bins = cv.take<uint32_t>(1024);
         idx = cv.take<uint32_t>((size_t)W * T * 4);
         if (j.rho) d_rho = cv.take<uint8_t>((size_t)o.fr_bytes * T);
         buckets = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W * B);
@@ -173,11 +199,12 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
             {
                 ProfScope ps("k_msm_sort", o.name, np, s);
                 msm_sort(sa, counts, s);
+                msm_order(counts, (uint64_t)W << c, bins, order, s);
             }
             MsmAccArgs aa;
             aa.aff1 = aff1;
             aa.inf1 = inf1;
-            aa.aff2 = two ? aff2 : aff1 + 1;  // power_pairs: v2_i = v1_{i+1} (same SoA stride)
+            aa.aff2 = two ? aff2 : aff1 + 2 * fw;  // power_pairs: v2_i = v1_{i+1} (next AoS element)
             aa.inf2 = two ? inf2 : inf1 + 1;
             aa.stride = stride;
             aa.n = np;
@@ -186,6 +213,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
             aa.offsets = hist;
             aa.counts = counts;
             aa.idx = idx;
+            aa.order = order;
             aa.buckets = buckets;
             ProfScope ps("k_msm_accumulate", o.name, np, s);
             mo->accumulate(aa, s);

@@ -32,6 +32,7 @@ struct Bls377G1 {
     using GP = Bls377G1Params;
     static constexpr int COORD_LIMBS = 12;
     static constexpr int USIZE = 96, CSIZE = 48;
+    static constexpr int SMUL_MINB = 4;  // k_scalar_mul blocks/SM: 128 regs, 16 warps/SM measured best (A/B in profiles/)
     static const char* name() { return "bls12_377.g1"; }
     SS_HD static F b() {
         F r;
@@ -56,6 +57,7 @@ struct Bls377G2 {
     using Fr = Fp<Bls377Fr>;
     using GP = Bls377G2Params;
     static constexpr int USIZE = 192, CSIZE = 96;
+    static constexpr int SMUL_MINB = 1;  // Fq2 needs the full 255 registers
     static const char* name() { return "bls12_377.g2"; }
     SS_HD static F b() {
         F r;
@@ -86,6 +88,7 @@ struct Bw6Group {
     using Fr = Fp<Bls377Fq>;  // BW6-761's scalar field is BLS12-377's base field
     using GP = GPx;
     static constexpr int USIZE = 192, CSIZE = 96;
+    static constexpr int SMUL_MINB = 1;
     static const char* name() { return GP::b(0) == Bw6G1Params::b(0) ? "bw6_761.g1" : "bw6_761.g2"; }
     SS_HD static F b() {
         F r;

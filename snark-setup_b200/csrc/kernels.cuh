@@ -40,6 +40,16 @@ struct FieldWords<Fp<P>> {
         for (int i = 0; i < P::N; i++) a.l[i] = base[i * stride];
         return a;
     }
+    SS_D static Fp<P> unpack(const uint32_t* w) {
+        Fp<P> a;
+#pragma unroll
+        for (int i = 0; i < P::N; i++) a.l[i] = w[i];
+        return a;
+    }
+    SS_D static void pack(uint32_t* w, const Fp<P>& a) {
+#pragma unroll
+        for (int i = 0; i < P::N; i++) w[i] = a.l[i];
+    }
 };
 template <class P>
 struct FieldWords<Fp2<P>> {
@@ -53,6 +63,13 @@ struct FieldWords<Fp2<P>> {
         a.c0 = FieldWords<Fp<P>>::load(base, stride);
         a.c1 = FieldWords<Fp<P>>::load(base + P::N * stride, stride);
         return a;
+    }
+    SS_D static Fp2<P> unpack(const uint32_t* w) {
+        return Fp2<P>{FieldWords<Fp<P>>::unpack(w), FieldWords<Fp<P>>::unpack(w + P::N)};
+    }
+    SS_D static void pack(uint32_t* w, const Fp2<P>& a) {
+        FieldWords<Fp<P>>::pack(w, a.c0);
+        FieldWords<Fp<P>>::pack(w + P::N, a.c1);
     }
 };
 
@@ -106,8 +123,20 @@ __global__ void k_powers(const uint32_t* __restrict__ tab, uint64_t start, uint6
     for (int k = 0; k < FrP::N; k++) out[i * FrP::N + k] = c.l[k];
 }
 
+template <class G>
+SS_D void store_affine(uint32_t* aff, uint64_t i, const Affine<typename G::F>& p) {
+    using FW = FieldWords<typename G::F>;
+    constexpr int W2 = 2 * FW::W;
+    uint32_t w[W2];
+    FW::pack(w, p.x);
+    FW::pack(w + FW::W, p.y);
+    uint4* dst = reinterpret_cast<uint4*>(aff + i * W2);
+#pragma unroll
+    for (int k = 0; k < W2 / 4; k++) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
 // ---- stage 1: read_batch ------------------------------------------------------------------------
-// Affine scratch `aff`: limb-major SoA [2*FW][n] (x then y, Montgomery) + one flag byte per element
+// Affine scratch `aff`: [n][2*FW] words (x then y, Montgomery) + one flag byte per element
 // (1 = point at infinity).
 struct DecodeArgs {
     const uint32_t* in;  // serialized elements
@@ -135,18 +164,32 @@ __global__ void __launch_bounds__(128) k_decode(DecodeArgs a) {
         p.x = F::zero();
         p.y = F::zero();
     }
-    FW::store(a.aff + i, a.n, p.x);
-    FW::store(a.aff + (uint64_t)FW::W * a.n + i, a.n, p.y);
+    store_affine<G>(a.aff, i, p);
     a.inf[i] = p.inf ? 1 : 0;
 }
 
+// The affine scratch is ARRAY-OF-STRUCTS: element i = 2*FW contiguous words (x then y), moved with
+// 16-byte vector accesses.  Per-element kernels read it as well coalesced as the SoA form would be
+// (a warp covers one contiguous 32*8*FW-byte span) and the MSM gathers — random element per lane —
+// touch 3 (6) full 32-byte sectors per point instead of 24 (48) partially used ones.
 template <class G>
-SS_D Affine<typename G::F> load_affine(const uint32_t* aff, const uint8_t* inf, uint64_t n, uint64_t i) {
+SS_D Affine<typename G::F> load_affine(const uint32_t* aff, const uint8_t* inf, uint64_t /*n*/, uint64_t i) {
     using F = typename G::F;
     using FW = FieldWords<F>;
+    constexpr int W2 = 2 * FW::W;
+    uint32_t w[W2];
+    const uint4* src = reinterpret_cast<const uint4*>(aff + i * W2);
+#pragma unroll
+    for (int k = 0; k < W2 / 4; k++) {
+        uint4 v = src[k];
+        w[4 * k] = v.x;
+        w[4 * k + 1] = v.y;
+        w[4 * k + 2] = v.z;
+        w[4 * k + 3] = v.w;
+    }
     Affine<F> p;
-    p.x = FW::load(aff + i, n);
-    p.y = FW::load(aff + (uint64_t)FW::W * n + i, n);
+    p.x = FW::unpack(w);
+    p.y = FW::unpack(w + FW::W);
     p.inf = inf[i] != 0;
     return p;
 }
@@ -169,11 +212,8 @@ struct ScalarMulArgs {
 #ifndef SS_SMUL_TPB
 #define SS_SMUL_TPB 128
 #endif
-#ifndef SS_SMUL_MINB
-#define SS_SMUL_MINB 1
-#endif
 template <class G>
-__global__ void __launch_bounds__(SS_SMUL_TPB, SS_SMUL_MINB) k_scalar_mul(ScalarMulArgs a) {
+__global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(ScalarMulArgs a) {
     using F = typename G::F;
     using FrP = typename G::Fr::Params;
     using FW = FieldWords<F>;

@@ -48,7 +48,7 @@ struct RhoSource {
     uint32_t key[8];               // ChaCha20 key when explicit_rho == nullptr
     uint64_t first_index;          // global index of element 0 (ChaCha counter base)
     int frw;                       // scalar words
-    int nbits;                     // scalar bits actually used (128 for generated, field bits for explicit)
+    int nbits;                     // scalar bits actually used (W*c >= 128 for generated, field bits for explicit)
 };
 
 // c-bit digit `w` of the scalar of element i
@@ -70,7 +70,7 @@ SS_D void rho_load(const RhoSource& r, uint64_t i, uint32_t* words /*[12]*/) {
     } else {
         uint32_t blk[16];
         chacha20_block(r.key, r.first_index + i, blk);
-        for (int k = 0; k < r.frw; k++) words[k] = k < 4 ? blk[k] : 0u;
+        for (int k = 0; k < r.frw; k++) words[k] = k < 5 ? blk[k] : 0u;  // up to 160 bits; nbits masks the rest
     }
 }
 
@@ -143,22 +143,43 @@ static __global__ void k_msm_scatter(MsmSortArgs a) {
 }
 
 // ---- bucket accumulators ------------------------------------------------------------------------
-// Layout: limb-major SoA [3*FW][NB] with NB = 2 * W * B  (first W*B: sum over v1, second: over v2).
+// Layout: [NB][3*FW] with NB = 2 * W * B  (first W*B entries: sums over v1, second: over v2).
+// Bucket / partial-sum arrays are ARRAY-OF-STRUCTS: entry i = 3*FW contiguous words (X, Y, Z), moved
+// with 16-byte vector accesses.  (The limb-major SoA form used elsewhere puts the 3*FW words of one
+// bucket 2*W*B*4 bytes apart; with buckets visited in sorted-by-run-length order that is 36 scattered
+// sectors per bucket and, for some power-of-two strides, pathological: 3.2 s instead of 9 ms for a
+// 2^19-element vector, profiles/r01_msm_layout.md.)  `stride` is kept in the signature for symmetry.
 template <class G>
-SS_D Jac<typename G::F> load_jac(const uint32_t* base, uint64_t stride, uint64_t i) {
+SS_D Jac<typename G::F> load_jac(const uint32_t* base, uint64_t /*stride*/, uint64_t i) {
     using FW = FieldWords<typename G::F>;
+    constexpr int W3 = 3 * FW::W;
+    uint32_t w[W3];
+    const uint4* src = reinterpret_cast<const uint4*>(base + i * W3);
+#pragma unroll
+    for (int k = 0; k < W3 / 4; k++) {
+        uint4 v = src[k];
+        w[4 * k] = v.x;
+        w[4 * k + 1] = v.y;
+        w[4 * k + 2] = v.z;
+        w[4 * k + 3] = v.w;
+    }
     Jac<typename G::F> j;
-    j.X = FW::load(base + i, stride);
-    j.Y = FW::load(base + (uint64_t)FW::W * stride + i, stride);
-    j.Z = FW::load(base + (uint64_t)2 * FW::W * stride + i, stride);
+    j.X = FW::unpack(w);
+    j.Y = FW::unpack(w + FW::W);
+    j.Z = FW::unpack(w + 2 * FW::W);
     return j;
 }
 template <class G>
-SS_D void store_jac(uint32_t* base, uint64_t stride, uint64_t i, const Jac<typename G::F>& j) {
+SS_D void store_jac(uint32_t* base, uint64_t /*stride*/, uint64_t i, const Jac<typename G::F>& j) {
     using FW = FieldWords<typename G::F>;
-    FW::store(base + i, stride, j.X);
-    FW::store(base + (uint64_t)FW::W * stride + i, stride, j.Y);
-    FW::store(base + (uint64_t)2 * FW::W * stride + i, stride, j.Z);
+    constexpr int W3 = 3 * FW::W;
+    uint32_t w[W3];
+    FW::pack(w, j.X);
+    FW::pack(w + FW::W, j.Y);
+    FW::pack(w + 2 * FW::W, j.Z);
+    uint4* dst = reinterpret_cast<uint4*>(base + i * W3);
+#pragma unroll
+    for (int k = 0; k < W3 / 4; k++) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
 }
 
 template <class G>
@@ -179,16 +200,23 @@ struct MsmAccArgs {
     const uint32_t* offsets;  // [W][B] exclusive offsets
     const uint32_t* counts;   // [W][B]
     const uint32_t* idx;      // [W][n]
+    const uint32_t* order;    // [W*B] bucket ids sorted by decreasing run length
     uint32_t* buckets;        // [3*FW][2*W*B]
 };
 
+#ifndef SS_MSM_MINB_NARROW
+#define SS_MSM_MINB_NARROW 3
+#endif
 template <class G>
-__global__ void __launch_bounds__(128) k_msm_accumulate(MsmAccArgs a) {
+__global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_MSM_MINB_NARROW)) k_msm_accumulate(MsmAccArgs a) {
     using F = typename G::F;
     const uint32_t B = 1u << a.c;
     const uint64_t WB = (uint64_t)a.W * B;
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= WB) return;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= WB) return;
+    // buckets are visited longest-run first: the lanes of a warp get runs of (nearly) equal length and the
+    // tail of the grid is made of the short ones
+    const uint64_t t = a.order[tid];
     const uint32_t d = (uint32_t)(t & (B - 1));
     const uint32_t cnt = a.counts[t];
     if (d == 0 || cnt == 0) return;
@@ -321,6 +349,37 @@ struct MsmLaunch {
     }
     static MsmOps ops() { return MsmOps{&fill_identity, &accumulate, &reduce}; }
 };
+
+// counting sort of the W*B buckets by decreasing run length (runs longer than 255 share the first bin)
+static __global__ void k_msm_order_hist(const uint32_t* counts, uint64_t wb, uint32_t* bins) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= wb) return;
+    uint32_t c = counts[t];
+    atomicAdd(&bins[255u - (c > 255u ? 255u : c)], 1u);
+}
+static __global__ void k_msm_order_scan(uint32_t* bins) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t run = 0;
+    for (int i = 0; i < 256; i++) {
+        uint32_t v = bins[i];
+        bins[i] = run;
+        run += v;
+    }
+}
+static __global__ void k_msm_order_scatter(const uint32_t* counts, uint64_t wb, uint32_t* bins, uint32_t* order) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= wb) return;
+    uint32_t c = counts[t];
+    uint32_t pos = atomicAdd(&bins[255u - (c > 255u ? 255u : c)], 1u);
+    order[pos] = (uint32_t)t;
+}
+
+static inline void msm_order(const uint32_t* counts, uint64_t wb, uint32_t* bins, uint32_t* order, cudaStream_t s) {
+    cudaMemsetAsync(bins, 0, 256 * 4, s);
+    k_msm_order_hist<<<(unsigned)((wb + 255) / 256), 256, 0, s>>>(counts, wb, bins);
+    k_msm_order_scan<<<1, 32, 0, s>>>(bins);
+    k_msm_order_scatter<<<(unsigned)((wb + 255) / 256), 256, 0, s>>>(counts, wb, bins, order);
+}
 
 static inline void msm_sort(const MsmSortArgs& a, uint32_t* counts, cudaStream_t s) {
     const uint32_t B = 1u << a.c;

@@ -1,7 +1,9 @@
 #!/bin/bash
-# A/B: run the contribute bench (no verify/cpu legs) for the default library and every variant
+# A/B: run the bench for the default library and every variant under snark-setup_b200/csrc/variants/
 cd "$(dirname "$0")/.."
-echo "== default"; python bench.py --no-cpu-baseline --no-verify --steps 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernels_ms_per_step'], d['parity_spot_check'])"
+summ='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print("contribute", round(d["value"]), round(d["ms_per_step"],1), "e2e", round(d["e2e"]["value"]), d["roofline"]["kernels_ms_per_step"], d["parity_spot_check"]); v=d.get("verify"); print("verify", round(v["value"]), round(v["ms_per_step"],1), v["ratio_and_reemit_check"], v["kernels_ms_per_step"]) if v else None'
+echo "== default"; python bench.py --no-cpu-baseline --steps 3 2>&1 | python -c "$summ"
 for v in snark-setup_b200/csrc/variants/*.so; do
-  echo "== $v"; SS_LIB=$PWD/$v python bench.py --no-cpu-baseline --no-verify --steps 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernels_ms_per_step'], d['parity_spot_check'])"
+  [ -e "$v" ] || continue
+  echo "== $v"; SS_LIB=$PWD/$v python bench.py --no-cpu-baseline --steps 3 2>&1 | python -c "$summ"
 done
