@@ -97,6 +97,7 @@ def run_reference(args, rank):
         return
     import coracle as O
     import pyref as R
+    O.set_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     cores = O.threads()
     k = args.ref_power
     p = R.Phase1Parameters(R.BLS12_377, k, 256)
@@ -127,6 +128,7 @@ def run_reference(args, rank):
 def cpu_baseline(budget_s=12.0):
     import coracle as O
     import pyref as R
+    O.set_threads(len(os.sched_getaffinity(0)))
     cores = O.threads()
     k0, k1 = keys(b"bench-0"), keys(b"bench-1")
 

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/snark_setup_b200.h"
@@ -489,23 +490,15 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
     for (const uint8_t* s : {tau, alpha, beta})
         if (!scalar_is_canonical(p->curve, s)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "scalar >= r");
     if ((rc = ensure_init())) return rc;
-    const int device = g_devices[0];
-    CU(cudaSetDevice(device));
-
-    LaneGuard setup_lane;
-    if ((rc = lane_acquire(device, 4096, &setup_lane.l))) return rc;
-    ScalarSetup sc;
-    const uint8_t* coeffs[3] = {nullptr, alpha, beta};
-    if ((rc = sc.init(g1, tau, coeffs, setup_lane.l->stream))) return rc;
-
     // split (buffers.rs:293-341): [hash][tau_g1][tau_g2][alpha_g1][beta_g1][beta_g2]
     auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
     const uint64_t n1 = z.g1_chunk_size, n2 = z.other_chunk_size;
+    const uint64_t cnt[5] = {n1, n2, n2, n2, 1};
+    const GroupOps* gs[5] = {&g1, &g2, &g1, &g1, &g2};
+    const char* names[5] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1", "beta_g2"};
     uint64_t oi[5], oo[5];
     {
         uint64_t a = 64, b = 64;
-        const uint64_t cnt[5] = {n1, n2, n2, n2, 1};
-        const GroupOps* gs[5] = {&g1, &g2, &g1, &g1, &g2};
         for (int v = 0; v < 5; v++) {
             oi[v] = a;
             oo[v] = b;
@@ -514,20 +507,56 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
         }
     }
     const uint64_t first = p->contribution_mode == SS_MODE_CHUNKED ? p->chunk_index * p->chunk_size : 0;
-    VectorJob jobs[5] = {
-        // tau_g1 <- tau^i
-        {&g1, input + oi[0], output + oo[0], cin, cout, check, n1, nullptr, sc.d_tab, first, sc.d_coeff_m[0], 0, "tau_g1"},
-        // tau_g2 <- tau^i
-        {&g2, input + oi[1], output + oo[1], cin, cout, check, n2, nullptr, sc.d_tab, first, sc.d_coeff_m[0], 0, "tau_g2"},
-        // alpha_g1 <- alpha tau^i
-        {&g1, input + oi[2], output + oo[2], cin, cout, check, n2, nullptr, sc.d_tab, first, sc.d_coeff_m[1], 1, "alpha_g1"},
-        // beta_g1 <- beta tau^i
-        {&g1, input + oi[3], output + oo[3], cin, cout, check, n2, nullptr, sc.d_tab, first, sc.d_coeff_m[2], 1, "beta_g1"},
-        // beta_g2 <- beta   (computation.rs:42-50): tau^0 * beta
-        {&g2, input + oi[4], output + oo[4], cin, cout, check, 1, nullptr, sc.d_tab, 0, sc.d_coeff_m[2], 1, "beta_g2"},
+
+    // One worker per device.  Every vector is cut into D equal contiguous parts (balance by
+    // work, not by index — indices >= 2^k only carry one G1 element); element i of a part still gets
+    // tau^(first + i) because each part passes its own first power.  No inter-device traffic.
+    const int D = host ? (int)g_devices.size() : 1;
+    auto worker = [&](int di, ss_error_info* err) -> int {
+        const int device = host ? g_devices[di] : g_devices[0];
+        auto run = [&]() -> int {
+            CU(cudaSetDevice(device));
+            LaneGuard setup_lane;
+            int r = lane_acquire(device, 4096, &setup_lane.l);
+            if (r) return r;
+            ScalarSetup sc;
+            const uint8_t* coeffs[3] = {nullptr, alpha, beta};
+            if ((r = sc.init(g1, tau, coeffs, setup_lane.l->stream))) return r;
+            const uint32_t* cm[5] = {sc.d_coeff_m[0], sc.d_coeff_m[0], sc.d_coeff_m[1], sc.d_coeff_m[2], sc.d_coeff_m[2]};
+            const int hc[5] = {0, 0, 1, 1, 1};
+            for (int v = 0; v < 5; v++) {
+                uint64_t s0 = 0, e0 = cnt[v];
+                if (v == 4) {
+                    if (di != 0) continue;  // beta_g2 <- beta * beta_g2 (computation.rs:42-50): tau^0 * beta
+                } else {
+                    const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
+                    s0 = di * base + std::min<uint64_t>(di, rem);
+                    e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
+                }
+                VectorJob job = {gs[v], input + oi[v] + s0 * sz(*gs[v], cin), output + oo[v] + s0 * sz(*gs[v], cout), cin,
+                                 cout, check, e0 - s0, nullptr, sc.d_tab, v == 4 ? 0 : first + s0, cm[v], hc[v], names[v]};
+                if ((r = run_vector_on(device, job, host, user_stream))) {
+                    g_err.index += s0;  // report vector-relative indices
+                    return r;
+                }
+            }
+            return SS_OK;
+        };
+        int r = run();
+        if (r && err) *err = g_err;
+        return r;
     };
-    for (int v = 0; v < 5; v++)
-        if ((rc = run_vector_on(device, jobs[v], host, user_stream))) return rc;
+    if (D == 1) return worker(0, nullptr);
+    std::vector<std::thread> th;
+    std::vector<int> rcs(D, SS_OK);
+    std::vector<ss_error_info> errs(D);
+    for (int di = 0; di < D; di++) th.emplace_back([&, di] { rcs[di] = worker(di, &errs[di]); });
+    for (auto& t : th) t.join();
+    for (int di = 0; di < D; di++)
+        if (rcs[di]) {
+            g_err = errs[di];
+            return rcs[di];
+        }
     return SS_OK;
 }
 

@@ -37,6 +37,8 @@ struct RatioJob {
     uint8_t* out_s;          // HOST: uncompressed s, sx
     uint8_t* out_sx;
     const char* what;
+    uint64_t rho_base = 0;   // global index of element 0 (ChaCha20 counter base) when the vector is a shard
+    uint64_t own = 0;        // elements to subgroup-check / re-emit (0 = all n); n - own = 1 overlap element of a shard
 };
 
 int pick_window_bits(uint64_t pairs_per_tile) {
@@ -71,8 +73,9 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     const size_t isz = j.compressed ? o.csize : o.usize, osz = j.out_compressed ? o.csize : o.usize;
     // ratio jobs use larger tiles than batch_exp: W*B bucket threads per tile must be several waves of the
     // machine (2^20 pairs -> c = 15 -> 9 x 32768 buckets), see profiles/r01_ncu_msm_accumulate.md
-    const size_t T = std::min<uint64_t>(j.do_ratio ? ratio_tile_elems() : tile_elems(), j.n);
-    const size_t ntiles = (j.n + T - 1) / T;
+    const uint64_t own_total = j.own ? j.own : j.n;
+    const size_t T = std::min<uint64_t>(j.do_ratio ? ratio_tile_elems() : tile_elems(), own_total);
+    const size_t ntiles = (own_total + T - 1) / T;
     // Window width c and scalar width.  Every window must be FULL: a top window of b < c bits has only
     // 2^b - 1 buckets holding n / 2^b points each, and one thread per bucket then serialises the whole
     // tile (measured: 3.2 s instead of 9 ms at n = 2^19, c = 14, 128-bit rho).  Generated rho therefore
@@ -146,7 +149,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
 
     for (size_t t = 0; t < ntiles; t++) {
         const uint64_t e0 = t * T;
-        const uint64_t own = std::min<uint64_t>(T, j.n - e0);                  // elements this tile owns
+        const uint64_t own = std::min<uint64_t>(T, own_total - e0);            // elements this tile owns
         const uint64_t ne = two ? own : std::min<uint64_t>(T + 1, j.n - e0);   // decoded (one overlap for power_pairs)
         const uint64_t np = j.do_ratio ? (two ? own : (e0 < pairs ? std::min<uint64_t>(T, pairs - e0) : 0)) : 0;
         const uint64_t stride = ne;
@@ -187,7 +190,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
             } else {
                 memcpy(sa.rho.key, j.seed, 32);
             }
-            sa.rho.first_index = e0;
+            sa.rho.first_index = j.rho_base + e0;
             sa.rho.frw = o.fr_words;
             sa.rho.nbits = nbits;
             sa.n = np;
@@ -326,27 +329,112 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
     const GroupOps* gs[5] = {&g1, &g2, &g1, &g1, &g2};
     const int grp[5] = {SS_G1, SS_G2, SS_G1, SS_G1, SS_G2};
     const char* names[5] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1", "beta_g2"};
-    uint64_t a = 64, b = 64, po = 0;
-    for (int v = 0; v < 5; v++) {
-        uint8_t* out = new_challenge ? new_challenge + b : nullptr;
-        if (cnt[v]) {
-            if (v < 4) {
-                // a vector of one element cannot be ratio-checked (verification.rs:238-241 -> BatchTooSmall)
-                if (ratio_check && cnt[v] < 2) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: batch too small", names[v]);
-                RatioJob j = {p->curve, grp[v], output + a, nullptr, compressed_output, SS_CHECK_ONLY_NON_ZERO, cnt[v],
-                              subgroup_mode != SS_SUBGROUP_NO, ratio_check, nullptr, rho_seed, out, compressed_new_challenge,
-                              pairs ? pairs + po : nullptr, pairs ? pairs + po + gs[v]->usize : nullptr, names[v]};
-                if ((rc = run_ratio_vector(g_devices[0], j, host, stream))) return rc;
-            } else if (out) {
-                // beta_g2: read with check_output_for_correctness (Full by default) and re-emit
-                RatioJob j = {p->curve, grp[v], output + a, nullptr, compressed_output, SS_CHECK_FULL, 1, 0, 0, nullptr, nullptr,
-                              out, compressed_new_challenge, nullptr, nullptr, names[v]};
-                if ((rc = run_ratio_vector(g_devices[0], j, host, stream))) return rc;
-            }
+    uint64_t oa[5], ob[5], op[5];
+    {
+        uint64_t a = 64, b = 64, po = 0;
+        for (int v = 0; v < 5; v++) {
+            oa[v] = a;
+            ob[v] = b;
+            op[v] = po;
+            po += 2 * (uint64_t)gs[v]->usize;
+            a += cnt[v] * sz(*gs[v], compressed_output);
+            b += cnt[v] * sz(*gs[v], compressed_new_challenge);
         }
-        po += 2 * (uint64_t)gs[v]->usize;
-        a += cnt[v] * sz(*gs[v], compressed_output);
-        b += cnt[v] * sz(*gs[v], compressed_new_challenge);
+    }
+    for (int v = 0; v < 4; v++)
+        // a vector of one element cannot be ratio-checked (verification.rs:238-241 -> BatchTooSmall)
+        if (ratio_check && cnt[v] == 1) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: batch too small", names[v]);
+
+    // One worker per device: device d takes the d-th contiguous part of every vector (plus one element of
+    // overlap for the ratio pairs, helpers.rs:388-390) and produces partial (s, sx); rho_i is indexed by
+    // the GLOBAL element index so the shards of one vector use disjoint ChaCha20 blocks.  The <= D partial
+    // points per vector are added on device 0 (k_sum_points); no other inter-device traffic.
+    const int D = host ? (int)g_devices.size() : 1;
+    std::vector<std::vector<uint8_t>> partial(D);
+    auto worker = [&](int di, ss_error_info* err) -> int {
+        const int device = host ? g_devices[di] : g_devices[0];
+        partial[di].assign(2 * (3 * (size_t)g1.usize + g2.usize), 0);
+        auto run = [&]() -> int {
+            for (int v = 0; v < 5; v++) {
+                if (!cnt[v]) continue;
+                uint8_t* out = new_challenge ? new_challenge + ob[v] : nullptr;
+                int r;
+                if (v == 4) {
+                    if (di != 0 || !out) continue;
+                    // beta_g2: read with check_output_for_correctness (Full by default) and re-emit
+                    RatioJob j = {p->curve, grp[v], output + oa[v], nullptr, compressed_output, SS_CHECK_FULL, 1, 0, 0, nullptr,
+                                  nullptr, out, compressed_new_challenge, nullptr, nullptr, names[v]};
+                    if ((r = run_ratio_vector(device, j, host, stream))) return r;
+                    continue;
+                }
+                // own elements [s0, e0); read one more when pairs continue into the next shard
+                const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
+                const uint64_t s0 = di * base + std::min<uint64_t>(di, rem), e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
+                if (e0 == s0) continue;
+                const bool last = e0 == cnt[v];
+                const uint64_t nread = (e0 - s0) + ((ratio_check && !last) ? 1 : 0);
+                const bool do_ratio = ratio_check && nread >= 2;
+                uint8_t* ps = partial[di].data() + op[v];
+                RatioJob j = {p->curve, grp[v], output + oa[v] + s0 * sz(*gs[v], compressed_output), nullptr, compressed_output,
+                              SS_CHECK_ONLY_NON_ZERO, nread, subgroup_mode != SS_SUBGROUP_NO, do_ratio, nullptr, rho_seed,
+                              out ? out + s0 * sz(*gs[v], compressed_new_challenge) : nullptr, compressed_new_challenge,
+                              ps, ps + gs[v]->usize, names[v], s0};
+                j.own = e0 - s0;
+                if ((r = run_ratio_vector(device, j, host, stream))) {
+                    g_err.index += s0;
+                    return r;
+                }
+                if (!do_ratio) {  // a one-element tail shard contributes the identity
+                    memset(ps, 0, 2 * (size_t)gs[v]->usize);
+                    ps[gs[v]->usize - 1] = 0x40;
+                    ps[2 * gs[v]->usize - 1] = 0x40;
+                }
+            }
+            return SS_OK;
+        };
+        int r = run();
+        if (r && err) *err = g_err;
+        return r;
+    };
+    if (D == 1) {
+        if ((rc = worker(0, nullptr))) return rc;
+        if (pairs) memcpy(pairs, partial[0].data(), partial[0].size());
+        return SS_OK;
+    }
+    std::vector<std::thread> th;
+    std::vector<int> rcs(D, SS_OK);
+    std::vector<ss_error_info> errs(D);
+    for (int di = 0; di < D; di++) th.emplace_back([&, di] { rcs[di] = worker(di, &errs[di]); });
+    for (auto& t : th) t.join();
+    for (int di = 0; di < D; di++)
+        if (rcs[di]) {
+            g_err = errs[di];
+            return rcs[di];
+        }
+    if (!ratio_check || !pairs) return SS_OK;
+    // add the partial sums on device 0
+    const int dev0 = g_devices[0];
+    CU(cudaSetDevice(dev0));
+    LaneGuard lg;
+    if ((rc = lane_acquire(dev0, 256 + (size_t)D * 192 + 192 + 256, &lg.l))) return rc;
+    cudaStream_t s = lg.l->stream;
+    unsigned long long* d_status = reinterpret_cast<unsigned long long*>(lg.l->buf);
+    uint8_t* d_in = lg.l->buf + 256;
+    uint8_t* d_out = d_in + align_up((size_t)D * 192, 256);
+    for (int v = 0; v < 4; v++) {
+        const size_t usz = gs[v]->usize;
+        for (int half = 0; half < 2; half++) {
+            std::vector<uint8_t> stage((size_t)D * usz);
+            for (int di = 0; di < D; di++) memcpy(stage.data() + di * usz, partial[di].data() + op[v] + half * usz, usz);
+            CU(cudaMemsetAsync(d_status, 0xff, 8, s));
+            CU(cudaMemcpyAsync(d_in, stage.data(), stage.size(), cudaMemcpyHostToDevice, s));
+            gs[v]->sum_points(reinterpret_cast<const uint32_t*>(d_in), D, reinterpret_cast<uint32_t*>(d_out), d_status, s);
+            CU(cudaMemcpyAsync(pairs + op[v] + half * usz, d_out, usz, cudaMemcpyDeviceToHost, s));
+            unsigned long long st;
+            CU(cudaMemcpyAsync(&st, d_status, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            if ((rc = decode_status(st, 0, "sum of partial ratio points"))) return rc;
+        }
     }
     return SS_OK;
 }

@@ -341,6 +341,32 @@ __global__ void __launch_bounds__(128) k_subgroup(SubgroupArgs a) {
     if (!in_subgroup<G>(p)) report(a.status, i, ERR_INCORRECT_SUBGROUP);
 }
 
+// ---- sum of a few uncompressed points (adds the per-device partial (s, sx) of a sharded ratio check) ----
+template <class G>
+__global__ void k_sum_points(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status) {
+    using F = typename G::F;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Jac<F> acc = Jac<F>::identity();
+    for (int i = 0; i < count; i++) {
+        Affine<F> p;
+        int e = decode_point<G>(pts + (size_t)i * (G::USIZE / 4), false, CHECK_NO, p);
+        if (e != ERR_OK) {
+            report(status, i, e);
+            return;
+        }
+        acc = jac_madd(acc, p);
+    }
+    Affine<F> r;
+    if (acc.is_identity()) {
+        r.inf = true;
+        r.x = F::zero();
+        r.y = F::zero();
+    } else {
+        r = jac_to_affine_with_zinv(acc, fp_inv(acc.Z));
+    }
+    encode_point<G>(out, false, r);
+}
+
 // ---- function table seen by api.cu -------------------------------------------------------------
 struct GroupOps {
     const char* name;      // e.g. "bls12_377.g1" (profiling labels)
@@ -356,6 +382,7 @@ struct GroupOps {
     void (*normalize_encode)(const NormalizeArgs&, cudaStream_t);
     void (*encode)(const EncodeArgs&, cudaStream_t);
     void (*subgroup)(const SubgroupArgs&, cudaStream_t);
+    void (*sum_points)(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status, cudaStream_t);
 };
 
 template <class G>
@@ -389,6 +416,9 @@ struct GroupLaunch {
         if (!a.count) return;
         k_subgroup<G><<<(unsigned)((a.count + 127) / 128), 128, 0, s>>>(a);
     }
+    static void sum_points(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status, cudaStream_t s) {
+        k_sum_points<G><<<1, 32, 0, s>>>(pts, count, out, status);
+    }
     static GroupOps ops() {
         GroupOps o;
         o.name = G::name();
@@ -404,6 +434,7 @@ struct GroupLaunch {
         o.decode = &decode;
         o.encode = &encode;
         o.subgroup = &subgroup;
+        o.sum_points = &sum_points;
         return o;
     }
 };
