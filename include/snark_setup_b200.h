@@ -92,6 +92,12 @@ void ss_profile_reset(void);
 uint64_t ss_profile_launches(void);
 int ss_profile_read(ss_profile_entry* out, int max_entries);
 
+/* Tuning knob: whether the tau_g1 / tau_g2 / alpha_g1 / beta_g1 / beta_g2 vectors of one
+ * ss_phase1_* call are processed concurrently (one internal stream each; default on, or
+ * $SS_CONCURRENT_VECTORS=0) — the reference spawns one rayon task per vector the same way
+ * (phase1/src/computation.rs:68-188).  Results are identical either way. */
+void ss_set_concurrent_vectors(int on);
+
 /* buffer_size::<C>(compression) — setup-utils/src/io/mod.rs:13-15 */
 size_t ss_element_size(int curve, int group, int compressed);
 size_t ss_scalar_size(int curve);

@@ -170,6 +170,17 @@ struct Lane {
 };
 std::vector<Lane*> g_lanes;
 
+std::atomic<int> g_concurrent{-1};  // -1: take $SS_CONCURRENT_VECTORS (default on)
+bool concurrent_vectors() {
+    int v = g_concurrent.load();
+    if (v < 0) {
+        const char* e = getenv("SS_CONCURRENT_VECTORS");
+        v = !(e && atoi(e) == 0);
+        g_concurrent.store(v);
+    }
+    return v != 0;
+}
+
 size_t tile_elems() {
     static size_t t = [] {
         const char* e = getenv("SS_TILE_LOG2");
@@ -524,10 +535,13 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
             if ((r = sc.init(g1, tau, coeffs, setup_lane.l->stream))) return r;
             const uint32_t* cm[5] = {sc.d_coeff_m[0], sc.d_coeff_m[0], sc.d_coeff_m[1], sc.d_coeff_m[2], sc.d_coeff_m[2]};
             const int hc[5] = {0, 0, 1, 1, 1};
-            for (int v = 0; v < 5; v++) {
+            // The five vectors run CONCURRENTLY, one host thread + lane (stream, scratch) each: the
+            // low-occupancy tails (batch normalisation, the single beta_g2 element) of one vector overlap the
+            // scalar multiplications of another.  SS_CONCURRENT_VECTORS=0 restores the sequential order.
+            auto one_vector = [&](int v) -> int {
                 uint64_t s0 = 0, e0 = cnt[v];
                 if (v == 4) {
-                    if (di != 0) continue;  // beta_g2 <- beta * beta_g2 (computation.rs:42-50): tau^0 * beta
+                    if (di != 0) return SS_OK;  // beta_g2 <- beta * beta_g2 (computation.rs:42-50): tau^0 * beta
                 } else {
                     const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
                     s0 = di * base + std::min<uint64_t>(di, rem);
@@ -535,11 +549,31 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
                 }
                 VectorJob job = {gs[v], input + oi[v] + s0 * sz(*gs[v], cin), output + oo[v] + s0 * sz(*gs[v], cout), cin,
                                  cout, check, e0 - s0, nullptr, sc.d_tab, v == 4 ? 0 : first + s0, cm[v], hc[v], names[v]};
-                if ((r = run_vector_on(device, job, host, user_stream))) {
-                    g_err.index += s0;  // report vector-relative indices
-                    return r;
-                }
+                int rv = run_vector_on(device, job, host, concurrent_vectors() ? nullptr : user_stream);
+                if (rv) g_err.index += s0;  // report vector-relative indices
+                return rv;
+            };
+            if (!concurrent_vectors()) {
+                for (int v = 0; v < 5; v++)
+                    if ((r = one_vector(v))) return r;
+                return SS_OK;
             }
+            if (user_stream) CU(cudaStreamSynchronize(user_stream));  // work enqueued before the call comes first
+            int rv[5] = {0, 0, 0, 0, 0};
+            ss_error_info ev[5];
+            std::vector<std::thread> vt;
+            for (int v = 0; v < 5; v++)
+                vt.emplace_back([&, v] {
+                    cudaSetDevice(device);
+                    rv[v] = one_vector(v);
+                    if (rv[v]) ev[v] = g_err;
+                });
+            for (auto& t : vt) t.join();
+            for (int v = 0; v < 5; v++)
+                if (rv[v]) {
+                    g_err = ev[v];
+                    return rv[v];
+                }
             return SS_OK;
         };
         int r = run();
@@ -622,6 +656,8 @@ int ss_profile_read(ss_profile_entry* out, int max_entries) {
     }
     return n;
 }
+
+void ss_set_concurrent_vectors(int on) { g_concurrent.store(on ? 1 : 0); }
 
 int ss_device_count(void) {
     int c = 0;

@@ -354,42 +354,69 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
     auto worker = [&](int di, ss_error_info* err) -> int {
         const int device = host ? g_devices[di] : g_devices[0];
         partial[di].assign(2 * (3 * (size_t)g1.usize + g2.usize), 0);
-        auto run = [&]() -> int {
-            for (int v = 0; v < 5; v++) {
-                if (!cnt[v]) continue;
-                uint8_t* out = new_challenge ? new_challenge + ob[v] : nullptr;
-                int r;
-                if (v == 4) {
-                    if (di != 0 || !out) continue;
-                    // beta_g2: read with check_output_for_correctness (Full by default) and re-emit
-                    RatioJob j = {p->curve, grp[v], output + oa[v], nullptr, compressed_output, SS_CHECK_FULL, 1, 0, 0, nullptr,
-                                  nullptr, out, compressed_new_challenge, nullptr, nullptr, names[v]};
-                    if ((r = run_ratio_vector(device, j, host, stream))) return r;
-                    continue;
-                }
-                // own elements [s0, e0); read one more when pairs continue into the next shard
-                const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
-                const uint64_t s0 = di * base + std::min<uint64_t>(di, rem), e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
-                if (e0 == s0) continue;
-                const bool last = e0 == cnt[v];
-                const uint64_t nread = (e0 - s0) + ((ratio_check && !last) ? 1 : 0);
-                const bool do_ratio = ratio_check && nread >= 2;
-                uint8_t* ps = partial[di].data() + op[v];
-                RatioJob j = {p->curve, grp[v], output + oa[v] + s0 * sz(*gs[v], compressed_output), nullptr, compressed_output,
-                              SS_CHECK_ONLY_NON_ZERO, nread, subgroup_mode != SS_SUBGROUP_NO, do_ratio, nullptr, rho_seed,
-                              out ? out + s0 * sz(*gs[v], compressed_new_challenge) : nullptr, compressed_new_challenge,
-                              ps, ps + gs[v]->usize, names[v], s0};
-                j.own = e0 - s0;
-                if ((r = run_ratio_vector(device, j, host, stream))) {
-                    g_err.index += s0;
-                    return r;
-                }
-                if (!do_ratio) {  // a one-element tail shard contributes the identity
-                    memset(ps, 0, 2 * (size_t)gs[v]->usize);
-                    ps[gs[v]->usize - 1] = 0x40;
-                    ps[2 * gs[v]->usize - 1] = 0x40;
-                }
+        auto one_vector = [&](int v) -> int {
+            if (!cnt[v]) return SS_OK;
+            cudaStream_t st = concurrent_vectors() ? nullptr : stream;
+            uint8_t* out = new_challenge ? new_challenge + ob[v] : nullptr;
+            int r;
+            if (v == 4) {
+                if (di != 0 || !out) return SS_OK;
+                // beta_g2: read with check_output_for_correctness (Full by default) and re-emit
+                RatioJob j = {p->curve, grp[v], output + oa[v], nullptr, compressed_output, SS_CHECK_FULL, 1, 0, 0, nullptr,
+                              nullptr, out, compressed_new_challenge, nullptr, nullptr, names[v]};
+                return run_ratio_vector(device, j, host, st);
             }
+            // own elements [s0, e0); read one more when pairs continue into the next shard
+            const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
+            const uint64_t s0 = di * base + std::min<uint64_t>(di, rem), e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
+            if (e0 == s0) return SS_OK;
+            const bool last = e0 == cnt[v];
+            const uint64_t nread = (e0 - s0) + ((ratio_check && !last) ? 1 : 0);
+            const bool do_ratio = ratio_check && nread >= 2;
+            uint8_t* ps = partial[di].data() + op[v];
+            RatioJob j = {p->curve, grp[v], output + oa[v] + s0 * sz(*gs[v], compressed_output), nullptr, compressed_output,
+                          SS_CHECK_ONLY_NON_ZERO, nread, subgroup_mode != SS_SUBGROUP_NO, do_ratio, nullptr, rho_seed,
+                          out ? out + s0 * sz(*gs[v], compressed_new_challenge) : nullptr, compressed_new_challenge,
+                          ps, ps + gs[v]->usize, names[v], s0};
+            j.own = e0 - s0;
+            if ((r = run_ratio_vector(device, j, host, st))) {
+                g_err.index += s0;
+                return r;
+            }
+            if (!do_ratio) {  // a one-element tail shard contributes the identity
+                memset(ps, 0, 2 * (size_t)gs[v]->usize);
+                ps[gs[v]->usize - 1] = 0x40;
+                ps[2 * gs[v]->usize - 1] = 0x40;
+            }
+            return SS_OK;
+        };
+        auto run = [&]() -> int {
+            if (!concurrent_vectors()) {
+                for (int v = 0; v < 5; v++) {
+                    int r = one_vector(v);
+                    if (r) return r;
+                }
+                return SS_OK;
+            }
+            // vectors run concurrently (one thread + lane each): the latency-bound MSM reductions of one vector
+            // overlap the subgroup / bucket kernels of the others
+            CU(cudaSetDevice(device));
+            if (stream) CU(cudaStreamSynchronize(stream));
+            int rv[5] = {0, 0, 0, 0, 0};
+            ss_error_info ev[5];
+            std::vector<std::thread> vt;
+            for (int v = 0; v < 5; v++)
+                vt.emplace_back([&, v] {
+                    cudaSetDevice(device);
+                    rv[v] = one_vector(v);
+                    if (rv[v]) ev[v] = g_err;
+                });
+            for (auto& t : vt) t.join();
+            for (int v = 0; v < 5; v++)
+                if (rv[v]) {
+                    g_err = ev[v];
+                    return rv[v];
+                }
             return SS_OK;
         };
         int r = run();

@@ -21,6 +21,14 @@ namespace ss {
 // lowest failing index wins: status = min over failures of (index << 8 | code)
 constexpr unsigned long long STATUS_OK = ~0ull;
 
+// minimum resident blocks per SM for the 12-limb (G1) instantiations; A/B-measured, see profiles/
+#ifndef SS_SUBGROUP_MINB_NARROW
+#define SS_SUBGROUP_MINB_NARROW 4
+#endif
+#ifndef SS_DECODE_MINB_NARROW
+#define SS_DECODE_MINB_NARROW 4
+#endif
+
 SS_D void report(unsigned long long* status, uint64_t index, int code) {
     atomicMin(status, (unsigned long long)((index << 8) | (uint64_t)code));
 }
@@ -150,7 +158,7 @@ struct DecodeArgs {
 
 // BatchDeserializer::read_batch (setup-utils/src/io/read.rs:110-135): one element per thread.
 template <class G>
-__global__ void __launch_bounds__(128) k_decode(DecodeArgs a) {
+__global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_DECODE_MINB_NARROW)) k_decode(DecodeArgs a) {
     using F = typename G::F;
     using FW = FieldWords<F>;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,7 +342,7 @@ struct SubgroupArgs {
 };
 
 template <class G>
-__global__ void __launch_bounds__(128) k_subgroup(SubgroupArgs a) {
+__global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_SUBGROUP_MINB_NARROW)) k_subgroup(SubgroupArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.count) return;
     Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);

@@ -140,6 +140,10 @@ def profile_read():
             for i in range(n)}
 
 
+def set_concurrent_vectors(on=True):
+    lib().ss_set_concurrent_vectors(int(on))
+
+
 def init(devices=None):
     devices = list(devices or [])
     arr = (C.c_int * max(1, len(devices)))(*devices)

@@ -57,6 +57,24 @@ __global__ void k_imad_wide_x(uint32_t* out, int iters, uint32_t seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+__global__ void k_imad_hi(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a[8], b = seed | 1, c = threadIdx.x;
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 0x9e3779b1u + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+    }
+    uint32_t r = 0;
+    for (int i = 0; i < 8; i++) r ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// BLS12-377 Fq with a compile-time INV = 0xffffffff: ptxas then emits the m*p products as separate
+// IMAD.X + IMAD.HI.U32.X pairs instead of IMAD.WIDE.U32.X (411 vs 305 IMAD-pipe instructions)
+struct Bls377FqSplit : Bls377Fq {
+    SS_HD static uint32_t inv() { return 0xffffffffu; }
+};
+
 __global__ void k_dfma(double* out, int iters, double seed) {
     double a[8], b = seed, c = 1.0 / 3.0;
     for (int i = 0; i < 8; i++) a[i] = threadIdx.x + i;
@@ -140,6 +158,8 @@ int main() {
         int blocks = sms * (2048 / tpb);
         double t = time_kernel([&] { k_imad<<<blocks, tpb>>>(out, iters, 12345); }, 5);
         printf("{\"bench\": \"imad\", \"threads_per_sm\": 2048, \"tpb\": %d, \"gops\": %.1f}\n", tpb, (double)blocks * tpb * iters * 8 / t * 1e-9);
+        t = time_kernel([&] { k_imad_hi<<<blocks, tpb>>>(out, iters, 12345); }, 5);
+        printf("{\"bench\": \"imad_hi\", \"threads_per_sm\": 2048, \"tpb\": %d, \"gops\": %.1f}\n", tpb, (double)blocks * tpb * iters * 8 / t * 1e-9);
         t = time_kernel([&] { k_imad_wide<<<blocks, tpb>>>((uint64_t*)out, iters, 12345); }, 5);
         printf("{\"bench\": \"imad_wide\", \"threads_per_sm\": 2048, \"tpb\": %d, \"gops\": %.1f}\n", tpb, (double)blocks * tpb * iters * 8 / t * 1e-9);
         t = time_kernel([&] { k_imad_wide_x<<<blocks, tpb>>>(out, iters, 12345); }, 5);
@@ -167,6 +187,8 @@ int main() {
         printf("{\"bench\": \"fp_mul\", \"mode\": \"%s\", \"limbs\": 8, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", mode, warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
         t = time_kernel([&] { k_fpmul<Bls377Fq><<<blocks, tpb>>>(out, it, 7); }, 3);
         printf("{\"bench\": \"fp_mul\", \"mode\": \"%s\", \"limbs\": 12, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", mode, warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
+        t = time_kernel([&] { k_fpmul<Bls377FqSplit><<<blocks, tpb>>>(out, it, 7); }, 3);
+        printf("{\"bench\": \"fp_mul_split_mp\", \"limbs\": 12, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
         t = time_kernel([&] { k_fpmul2<Bls377Fq><<<blocks, tpb>>>(out, it, 7); }, 3);
         printf("{\"bench\": \"fp_mul_ilp2_inline\", \"limbs\": 12, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", warps_per_sm, (double)blocks * tpb * it * 2 / t * 1e-9);
         if (warps_per_sm <= 32) {
