@@ -183,6 +183,10 @@ typedef struct {
 
 int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out);
 
+/* iter_chunk — phase1/src/helpers/buffers.rs:22-73: the window schedule (start, end) of the reference's
+ * batch loop (windows overlap by one element).  starts/ends may be NULL to query *count only. */
+int ss_phase1_iter_chunk(const ss_phase1_params* p, uint64_t* starts, uint64_t* ends, size_t max_windows, size_t* count);
+
 /* Phase1::computation — phase1/src/computation.rs:16-308 (Groth16 branch :40-193).
  * input/output are the whole challenge / response buffers including the 64-byte hash prefix
  * (which is not touched, as in the reference); tau/alpha/beta = PrivateKey scalars. */

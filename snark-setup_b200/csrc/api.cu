@@ -823,6 +823,45 @@ int ss_check_subgroup(int curve, int group, const uint8_t* in, int compressed, s
 
 int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out) { return phase1_sizes(p, out); }
 
+// iter_chunk — phase1/src/helpers/buffers.rs:22-73: the reference's window schedule (windows of
+// batch_size elements, consecutive windows overlapping by one).  Host index arithmetic only; the engine
+// itself tiles whole vectors, this is exported for callers that keep the reference's loop structure.
+int ss_phase1_iter_chunk(const ss_phase1_params* p, uint64_t* starts, uint64_t* ends, size_t max_windows, size_t* count) {
+    ss_phase1_sizes z;
+    int rc = phase1_sizes(p, &z);
+    if (rc) return rc;
+    if (!count) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null count");
+    if (p->batch_size < 2) return fail(SS_ERR_INVALID_CHUNK, 0, 0, 0, "batch_size must be at least 2");
+    const uint64_t upper = p->proving_system == SS_GROTH16 ? z.powers_g1_length : z.powers_length;
+    uint64_t lo = 0, hi = upper;
+    if (p->contribution_mode == SS_MODE_CHUNKED) {
+        lo = p->chunk_index * p->chunk_size;
+        hi = std::min<uint64_t>((p->chunk_index + 1) * p->chunk_size, upper);
+    }
+    const uint64_t step = p->batch_size - 1;
+    size_t n = 0;
+    auto emit = [&](uint64_t s, uint64_t e) {
+        if (n < max_windows && starts && ends) {
+            starts[n] = s;
+            ends[n] = e;
+        }
+        n++;
+    };
+    for (uint64_t i = lo; i < hi; i += step) {
+        const uint64_t last = std::min<uint64_t>(i + step, hi) - 1;  // last index of this group
+        if (last > i) {
+            emit(i, last >= hi - 1 ? last + 1 : last + 2);
+        } else if (i >= hi - 1) {
+            if (hi == lo + 1) emit(i, i + 1);  // a single trailing element was already covered by the overlap
+        } else {
+            emit(i, i + 2);
+        }
+    }
+    *count = n;
+    if (n > max_windows && starts) return fail(SS_ERR_INVALID_LENGTH, 0, n, max_windows, "window buffer too small");
+    return SS_OK;
+}
+
 int ss_phase1_computation(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
                           size_t output_len, int compressed_input, int compressed_output, int check_input,
                           const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta) {

@@ -237,6 +237,57 @@ Jac<typename G::F> jac_mul_ladder_cold(Affine<typename G::F> base, const uint32_
     return jac_mul_bits<typename G::F>(base, [&](int i) { return k[i]; }, G::Fr::Params::BITS);
 }
 
+// One window of the main loop: 4 doublings, then for each sub-scalar one mixed addition of the (endomorphism
+// image of the) table entry selected by its signed digit.  For the wide fields this is ONE out-of-line function
+// (with the doubling and the addition inlined once each) so the accumulator crosses a call boundary once per
+// window instead of once per group operation: as separate calls the by-value Jacobian arguments cost
+// ~1300 words of local-memory traffic per window and k_scalar_mul<G2> stalled on them (3100 local
+// loads/stores per thread, fmaheavy pipe 75 % active; profiles/r01_ncu_full_v3.json).
+template <class G>
+SS_HD void endo_window_inl(Jac<typename G::F>& acc, const typename G::F* tx, const typename G::F* ty, const int8_t* dig,
+                           int i, bool first) {
+    using F = typename G::F;
+    using E = Endo<G>;
+    if (!first) {
+#pragma unroll 1
+        for (int d = 0; d < 4; d++) acc = jac_dbl_inl(acc);
+    }
+#pragma unroll 1
+    for (int j = 0; j < E::DIMS; j++) {
+        const int d = dig[j * E::ND + i];
+        if (d != 0) {
+            const int a = d < 0 ? -d : d;
+            Affine<F> q;
+            q.x = tx[a - 1];
+            q.y = ty[a - 1];
+            q.inf = false;
+            E::apply(j, q.x, q.y);
+            if (d < 0) q.y = fp_neg(q.y);
+            acc = jac_madd_inl(acc, q);
+        }
+    }
+}
+#if defined(__CUDACC__)
+template <class G>
+__device__ __noinline__ void endo_window_call(Jac<typename G::F>* acc, const typename G::F* tx, const typename G::F* ty,
+                                              const int8_t* dig, int i, int first) {
+    Jac<typename G::F> a = *acc;
+    endo_window_inl<G>(a, tx, ty, dig, i, first != 0);
+    *acc = a;
+}
+#endif
+template <class G>
+SS_HD void endo_window(Jac<typename G::F>& acc, const typename G::F* tx, const typename G::F* ty, const int8_t* dig, int i,
+                       bool first) {
+#if defined(__CUDA_ARCH__) && !defined(SS_GROUP_INLINE)
+    if constexpr (G::F::CALL_GROUP_OPS) {
+        endo_window_call<G>(&acc, tx, ty, dig, i, first ? 1 : 0);
+        return;
+    }
+#endif
+    endo_window_inl<G>(acc, tx, ty, dig, i, first);
+}
+
 // ---- k * P ----------------------------------------------------------------------------------------
 // `k` canonical little-endian words (G::Fr::N of them), k < r.
 template <class G>
@@ -287,26 +338,7 @@ SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, cons
     int8_t dig[DIMS * ND];
     E::decompose(k, dig);
     Jac<F> acc = Jac<F>::identity();
-    for (int i = ND - 1; i >= 0; i--) {
-        if (i != ND - 1) {
-#pragma unroll 1
-            for (int d = 0; d < 4; d++) acc = jac_dbl(acc);
-        }
-#pragma unroll 1
-        for (int j = 0; j < DIMS; j++) {
-            int d = dig[j * ND + i];
-            if (d != 0) {
-                int a = d < 0 ? -d : d;
-                Affine<F> q;
-                q.x = tx[a - 1];
-                q.y = ty[a - 1];
-                q.inf = false;
-                E::apply(j, q.x, q.y);
-                if (d < 0) q.y = fp_neg(q.y);
-                acc = jac_madd(acc, q);
-            }
-        }
-    }
+    for (int i = ND - 1; i >= 0; i--) endo_window<G>(acc, tx, ty, dig, i, i == ND - 1);
     acc.Z = fp_mul(acc.Z, zfinal);
     return acc;
 }

@@ -373,6 +373,16 @@ class Phase1Parameters:
     def get_length(self, compressed):
         return self.contribution_size - self.public_key_size if compressed else self.accumulator_size
 
+    def iter_chunk(self):
+        """phase1/src/helpers/buffers.rs:22-73 -> [(start, end)]."""
+        f = lib().ss_phase1_iter_chunk
+        f.argtypes = [C.POINTER(_P1Params), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]
+        cnt = C.c_size_t(0)
+        _check(f(C.byref(self.c), None, None, 0, C.byref(cnt)))
+        a, b = (C.c_uint64 * max(1, cnt.value))(), (C.c_uint64 * max(1, cnt.value))()
+        _check(f(C.byref(self.c), a, b, cnt.value, C.byref(cnt)))
+        return [(a[i], b[i]) for i in range(cnt.value)]
+
 
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
                        tau, alpha, beta):

@@ -58,3 +58,15 @@ def test_no_cpu_fallback():
         S.generate_powers_of_tau(S.BLS12_377, 5, 0, 4)
     with pytest.raises(S.DeviceError):
         S.apply_powers(S.BLS12_377, S.G1, bytes(96), False, S.CHECK_NO, True, 1, tau=3)
+
+
+def test_iter_chunk_matches_reference_schedule():
+    """phase1/src/helpers/buffers.rs:22-73 against the oracle restatement, incl. the SURVEY A5 example."""
+    for cid, cv in ((S.BLS12_377, R.BLS12_377),):
+        for k, bs, mode, ci, cs in ((10, 256, 0, 0, 0), (3, 4, 0, 0, 0), (4, 5, 1, 0, 8), (4, 5, 1, 1, 8), (4, 5, 1, 3, 8),
+                                    (4, 2, 0, 0, 0), (5, 7, 1, 2, 20), (4, 16, 1, 3, 8), (2, 64, 0, 0, 0)):
+            a = S.Phase1Parameters(cid, k, bs, mode, ci, cs).iter_chunk()
+            b = R.iter_chunk(R.Phase1Parameters(cv, k, bs, mode, ci, cs))
+            assert a == b, (k, bs, mode, ci, cs)
+    w = S.Phase1Parameters(S.BLS12_377, 10, 256).iter_chunk()
+    assert len(w) == 9 and w[0] == (0, 256) and w[1] == (255, 511) and w[-1] == (2040, 2047)

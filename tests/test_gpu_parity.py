@@ -144,3 +144,27 @@ def test_phase1_computation_bls12_377(power, batch):
             out = bytearray(sp.get_length(cout))
             S.phase1_computation(sp, acc, out, cin, cout, S.CHECK_NO, tau, alpha, beta)
             assert bytes(out) == bytes(want), (cin, cout)
+
+
+@pytest.mark.parametrize("chunk_index", [0, 1, 2, 3])
+def test_phase1_computation_chunked_mode(chunk_index):
+    """ContributionMode::Chunked (phase1/src/objects/parameters.rs:248-294; computation.rs:60-66): chunk c of
+    size 8 of a 2^4-power ceremony; element j of the chunk gets tau^(c*8 + j); chunks >= 2^k hold tau_g1 only."""
+    cv = R.BLS12_377
+    power, batch, csz = 4, 5, 8
+    rng = random.Random(40 + chunk_index)
+    rp = R.Phase1Parameters(cv, power, batch, R.CHUNKED_MODE, chunk_index, csz)
+    sp = S.Phase1Parameters(S.BLS12_377, power, batch, 1, chunk_index, csz)
+    assert (sp.g1_chunk_size, sp.other_chunk_size) == (rp.g1_chunk_size, rp.other_chunk_size)
+    assert sp.accumulator_size == rp.accumulator_size and sp.contribution_size == rp.contribution_size
+    tau, alpha, beta = (rng.randrange(2, cv.r) for _ in range(3))
+    # a chunk-shaped input of distinct points
+    acc = bytearray(rp.get_length(False))
+    for vec, (o, c, s) in enumerate(rp.split_offsets(False)):
+        g = cv.g2 if vec in (1, 4) else cv.g1
+        pts = [g.mul(g.gen, rng.randrange(1, cv.r)) for _ in range(c)]
+        acc[o:o + c * s] = g.write_batch(pts, False)
+    want = R.phase1_computation(rp, bytes(acc), False, True, R.NO, tau, alpha, beta)
+    out = bytearray(sp.get_length(True))
+    S.phase1_computation(sp, bytes(acc), out, False, True, S.CHECK_NO, tau, alpha, beta)
+    assert bytes(out) == bytes(want)
