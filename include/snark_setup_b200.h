@@ -214,6 +214,21 @@ int ss_phase1_verification_vectors(const ss_phase1_params* p, const uint8_t* out
                                    int compressed_new_challenge, int subgroup_mode, int ratio_check,
                                    const uint8_t* rho_seed, uint8_t* pairs);
 
+/* Accumulator re-layout — read_batch(CheckForCorrectness::No) -> write_batch streams:
+ *   ss_phase1_aggregate_chunk — one iteration of Phase1::aggregation (phase1/src/aggregation.rs:11-180): the
+ *     vectors of chunk `chunk_params->chunk_index` are written into the full accumulator at
+ *     chunk_index*chunk_size (beta_g2 comes from chunk 0);
+ *   ss_phase1_split_chunk — one iteration of Phase1::split (aggregation.rs:189-353), the reverse;
+ *   ss_phase1_decompress — helpers::accumulator::decompress (accumulator.rs:200-301): compressed
+ *     accumulator -> uncompressed, elements read with `check`.
+ * `chunk_params` must be in SS_MODE_CHUNKED; `full` is laid out for the same power in full mode.  The
+ * 64-byte hash prefixes are not touched. */
+int ss_phase1_aggregate_chunk(const ss_phase1_params* chunk_params, const uint8_t* chunk, size_t chunk_len, int compressed_chunk,
+                              uint8_t* full, size_t full_len, int compressed_full);
+int ss_phase1_split_chunk(const ss_phase1_params* chunk_params, const uint8_t* full, size_t full_len, int compressed_full,
+                          uint8_t* chunk, size_t chunk_len, int compressed_chunk);
+int ss_phase1_decompress(const ss_phase1_params* p, const uint8_t* in, size_t in_len, int check, uint8_t* out, size_t out_len);
+
 /* Same on buffers resident in device memory (`pairs` and rho_seed stay host pointers). */
 int ss_phase1_verification_vectors_dev(const ss_phase1_params* p, const void* d_output, size_t output_len,
                                        int compressed_output, void* d_new_challenge, size_t new_challenge_len,

@@ -39,7 +39,10 @@ from .ffi import (  # noqa: F401
     generate_powers_of_tau,
     lib,
     lib_path,
+    phase1_aggregate_chunk,
     phase1_computation,
+    phase1_decompress,
+    phase1_split_chunk,
     phase1_computation_dev,
     scalar_size,
     transcode,

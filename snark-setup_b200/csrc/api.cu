@@ -821,6 +821,101 @@ int ss_check_subgroup(int curve, int group, const uint8_t* in, int compressed, s
     return transcode_impl(curve, group, in, compressed, SS_CHECK_NO, nullptr, 0, n, subgroup_mode != SS_SUBGROUP_NO);
 }
 
+// ---- accumulator re-layout: aggregation / split / decompress ----------------------------------------
+// All three are read_batch(CheckForCorrectness) -> write_batch streams over the five vectors with different
+// source / destination offsets (phase1/src/aggregation.rs:11-180,189-353; helpers/accumulator.rs:182-301).
+static int copy_vectors(int curve, const uint8_t* src, const uint64_t* so, int src_c, uint8_t* dst, const uint64_t* dof,
+                        int dst_c, const uint64_t* cnt, int check) {
+    const int grp[5] = {SS_G1, SS_G2, SS_G1, SS_G1, SS_G2};
+    for (int v = 0; v < 5; v++) {
+        if (!cnt[v]) continue;
+        int rc = transcode_impl(curve, grp[v], src + so[v], src_c, check, dst + dof[v], dst_c, cnt[v], false);
+        if (rc) return rc;
+    }
+    return SS_OK;
+}
+
+// byte offsets of the five vectors in a buffer laid out for `z` (buffers.rs:293-341)
+static void vector_offsets(int curve, const ss_phase1_sizes& z, int compressed, uint64_t* off) {
+    const GroupOps& g1 = *group_ops(curve, SS_G1);
+    const GroupOps& g2 = *group_ops(curve, SS_G2);
+    const uint64_t s1 = compressed ? g1.csize : g1.usize, s2 = compressed ? g2.csize : g2.usize;
+    off[0] = 64;
+    off[1] = off[0] + z.g1_chunk_size * s1;
+    off[2] = off[1] + z.other_chunk_size * s2;
+    off[3] = off[2] + z.other_chunk_size * s1;
+    off[4] = off[3] + z.other_chunk_size * s1;
+}
+
+static int chunk_vs_full(const ss_phase1_params* cp, int compressed_chunk, int compressed_full, size_t chunk_len, size_t full_len,
+                         uint64_t* coff, uint64_t* foff, uint64_t* cnt) {
+    if (!cp) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (cp->proving_system != SS_GROTH16) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "only the Groth16 layout is implemented");
+    if (cp->contribution_mode != SS_MODE_CHUNKED) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "chunk parameters expected");
+    ss_phase1_params fp = *cp;
+    fp.contribution_mode = SS_MODE_FULL;
+    fp.chunk_index = 0;
+    ss_phase1_sizes cz, fz;
+    int rc = phase1_sizes(cp, &cz);
+    if (rc) return rc;
+    if ((rc = phase1_sizes(&fp, &fz))) return rc;
+    const GroupOps& g1 = *group_ops(cp->curve, SS_G1);
+    const GroupOps& g2 = *group_ops(cp->curve, SS_G2);
+    const uint64_t need_c = compressed_chunk ? cz.contribution_size - cz.public_key_size : cz.accumulator_size;
+    const uint64_t need_f = compressed_full ? fz.contribution_size - fz.public_key_size : fz.accumulator_size;
+    if (chunk_len < need_c) return fail(SS_ERR_INVALID_LENGTH, 0, need_c, chunk_len, "chunk buffer too short");
+    if (full_len < need_f) return fail(SS_ERR_INVALID_LENGTH, 0, need_f, full_len, "full buffer too short");
+    vector_offsets(cp->curve, cz, compressed_chunk, coff);
+    vector_offsets(cp->curve, fz, compressed_full, foff);
+    // split_at_chunk(_mut): the chunk starts chunk_index * chunk_size elements into every vector
+    const uint64_t first = cp->chunk_index * cp->chunk_size;
+    const uint64_t s1 = compressed_full ? g1.csize : g1.usize, s2 = compressed_full ? g2.csize : g2.usize;
+    foff[0] += first * s1;
+    foff[1] += first * s2;
+    foff[2] += first * s1;
+    foff[3] += first * s1;
+    cnt[0] = cz.g1_chunk_size;
+    cnt[1] = cnt[2] = cnt[3] = cz.other_chunk_size;
+    cnt[4] = cp->chunk_index == 0 ? 1 : 0;  // beta_g2 travels with chunk 0 (aggregation.rs:103-111)
+    return SS_OK;
+}
+
+int ss_phase1_aggregate_chunk(const ss_phase1_params* chunk_params, const uint8_t* chunk, size_t chunk_len, int compressed_chunk,
+                              uint8_t* full, size_t full_len, int compressed_full) {
+    uint64_t coff[5], foff[5], cnt[5];
+    int rc = chunk_vs_full(chunk_params, compressed_chunk, compressed_full, chunk_len, full_len, coff, foff, cnt);
+    if (rc) return rc;
+    if (!chunk || !full) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null buffer");
+    return copy_vectors(chunk_params->curve, chunk, coff, compressed_chunk, full, foff, compressed_full, cnt, SS_CHECK_NO);
+}
+
+int ss_phase1_split_chunk(const ss_phase1_params* chunk_params, const uint8_t* full, size_t full_len, int compressed_full,
+                          uint8_t* chunk, size_t chunk_len, int compressed_chunk) {
+    uint64_t coff[5], foff[5], cnt[5];
+    int rc = chunk_vs_full(chunk_params, compressed_chunk, compressed_full, chunk_len, full_len, coff, foff, cnt);
+    if (rc) return rc;
+    if (!chunk || !full) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null buffer");
+    cnt[4] = 1;  // every chunk file gets beta_g2 (aggregation.rs:278-284 writes it unconditionally)
+    return copy_vectors(chunk_params->curve, full, foff, compressed_full, chunk, coff, compressed_chunk, cnt, SS_CHECK_NO);
+}
+
+int ss_phase1_decompress(const ss_phase1_params* p, const uint8_t* in, size_t in_len, int check, uint8_t* out, size_t out_len) {
+    if (!p || !in || !out) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (p->proving_system != SS_GROTH16) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "only the Groth16 layout is implemented");
+    if (check < 0 || check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode");
+    ss_phase1_sizes z;
+    int rc = phase1_sizes(p, &z);
+    if (rc) return rc;
+    if (in_len < z.contribution_size - z.public_key_size)
+        return fail(SS_ERR_INVALID_LENGTH, 0, z.contribution_size - z.public_key_size, in_len, "compressed buffer too short");
+    if (out_len < z.accumulator_size) return fail(SS_ERR_INVALID_LENGTH, 0, z.accumulator_size, out_len, "output buffer too short");
+    uint64_t io[5], oo[5];
+    vector_offsets(p->curve, z, 1, io);
+    vector_offsets(p->curve, z, 0, oo);
+    const uint64_t cnt[5] = {z.g1_chunk_size, z.other_chunk_size, z.other_chunk_size, z.other_chunk_size, 1};
+    return copy_vectors(p->curve, in, io, 1, out, oo, 0, cnt, check);
+}
+
 int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out) { return phase1_sizes(p, out); }
 
 // iter_chunk — phase1/src/helpers/buffers.rs:22-73: the reference's window schedule (windows of

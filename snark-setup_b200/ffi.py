@@ -384,6 +384,37 @@ class Phase1Parameters:
         return [(a[i], b[i]) for i in range(cnt.value)]
 
 
+def phase1_aggregate_chunk(chunk_params, chunk, compressed_chunk, full: bytearray, compressed_full):
+    """One iteration of Phase1::aggregation (phase1/src/aggregation.rs:11-180); `full` is written in place."""
+    f = lib().ss_phase1_aggregate_chunk
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    pc, k1 = _buf(chunk)
+    pf, k2 = _buf(full)
+    _check(f(C.byref(chunk_params.c), pc, len(chunk), int(compressed_chunk), pf, len(full), int(compressed_full)))
+
+
+def phase1_split_chunk(chunk_params, full, compressed_full, compressed_chunk):
+    """One iteration of Phase1::split (phase1/src/aggregation.rs:189-353) -> chunk bytes (hash prefix zero)."""
+    f = lib().ss_phase1_split_chunk
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    out = bytearray(chunk_params.get_length(compressed_chunk))
+    pf, k1 = _buf(full)
+    pc, k2 = _buf(out)
+    _check(f(C.byref(chunk_params.c), pf, len(full), int(compressed_full), pc, len(out), int(compressed_chunk)))
+    return bytes(out)
+
+
+def phase1_decompress(params, inp, check=CHECK_NO):
+    """helpers::accumulator::decompress (phase1/src/helpers/accumulator.rs:200-301)."""
+    f = lib().ss_phase1_decompress
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+    out = bytearray(params.get_length(False))
+    pi, k1 = _buf(inp)
+    po, k2 = _buf(out)
+    _check(f(C.byref(params.c), pi, len(inp), check, po, len(out)))
+    return bytes(out)
+
+
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
                        tau, alpha, beta):
     """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place."""

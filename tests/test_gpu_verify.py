@@ -189,3 +189,39 @@ def test_phase1_contribute_then_verify(cid, cv):
     bad[o + 3 * sz:o + 4 * sz] = cv.g2.encode(None, True)
     with pytest.raises(S.PointAtInfinity):
         S.phase1_verification_vectors(sp, bytes(bad), True, None, False, seed=seed)
+
+
+def test_aggregation_split_decompress():
+    """phase1/src/aggregation.rs:355-846 shape: full accumulator -> split into chunks -> aggregate back, in
+    every compression combination, plus decompress (helpers/accumulator.rs:352-388 round trip)."""
+    cv, cid = R.BLS12_377, S.BLS12_377
+    power, batch, csz = 4, 8, 8
+    rng = random.Random(321)
+    rp = R.Phase1Parameters(cv, power, batch)
+    sp = S.Phase1Parameters(cid, power, batch)
+    keys = [rng.randrange(2, cv.r) for _ in range(3)]
+    full_u = O.phase1_computation(0, bytes(R.phase1_initialization(rp, False)), rp.get_length(False), False, False, 3,
+                                  rp.g1_chunk_size, rp.other_chunk_size, 0, *keys)
+    full_c = bytearray(rp.get_length(True))  # the same accumulator, compressed (oracle transcode per vector)
+    for vec, ((o, c, sz), (co, cc, csz_)) in enumerate(zip(rp.split_offsets(False), rp.split_offsets(True))):
+        full_c[co:co + cc * csz_] = O.transcode(0, 1 if vec in (1, 4) else 0, full_u[o:o + c * sz], False, 3, True, c)
+    full_c = bytes(full_c)
+    assert S.phase1_decompress(sp, full_c)[64:] == full_u[64:]
+    nchunks = (rp.powers_g1_length + csz - 1) // csz
+    for comp_full, full in ((False, full_u), (True, full_c)):
+        offs_full = rp.split_offsets(comp_full)
+        for comp_chunk in (False, True):
+            rebuilt = bytearray(len(full))
+            for ci in range(nchunks):
+                cp_r = R.Phase1Parameters(cv, power, batch, R.CHUNKED_MODE, ci, csz)
+                cp_s = S.Phase1Parameters(cid, power, batch, 1, ci, csz)
+                chunk = S.phase1_split_chunk(cp_s, full, comp_full, comp_chunk)
+                # expected chunk: slices of the full vectors, transcoded by the oracle
+                for vec, ((o, c, sz), (fo, fc, fsz)) in enumerate(zip(cp_r.split_offsets(comp_chunk), offs_full)):
+                    grp = 1 if vec in (1, 4) else 0
+                    first = 0 if vec == 4 else ci * csz
+                    src = full[fo + first * fsz:fo + (first + c) * fsz]
+                    want = O.transcode(0, grp, src, comp_full, 3, comp_chunk, c) if c else b""
+                    assert chunk[o:o + c * sz] == want, (comp_full, comp_chunk, ci, vec)
+                S.phase1_aggregate_chunk(cp_s, chunk, comp_chunk, rebuilt, comp_full)
+            assert bytes(rebuilt[64:]) == full[64:], (comp_full, comp_chunk)
