@@ -569,13 +569,19 @@ class Phase1Parameters:
         return self.contribution_size - self.public_key_size if compressed else self.accumulator_size
 
     def split_offsets(self, compressed):
-        """(offset, count, element_size) of [TauG1, TauG2, AlphaG1, BetaG1, BetaG2] (buffers.rs:293-341), Groth16."""
-        assert self.proving_system == GROTH16
+        """(offset, count, element_size) of [TauG1, TauG2, AlphaG1, BetaG1, BetaG2] (buffers.rs:293-341).
+        Marlin: [TauG1, TauG2 (k+2), AlphaG1 (3+3k)] on chunk 0, TauG1 only elsewhere; BetaG1/BetaG2 empty."""
         g1, g2 = self.curve.g1.size(compressed), self.curve.g2.size(compressed)
         o = self.hash_size
         out = []
-        for cnt, sz in ((self.g1_chunk_size, g1), (self.other_chunk_size, g2), (self.other_chunk_size, g1),
-                        (self.other_chunk_size, g1), (1, g2)):
+        if self.proving_system == MARLIN:
+            k = self.total_size_in_log2
+            first = self.chunk_index == 0
+            counts = ((self.g1_chunk_size, g1), ((k + 2) if first else 0, g2), ((3 + 3 * k) if first else 0, g1), (0, g1), (0, g2))
+        else:
+            counts = ((self.g1_chunk_size, g1), (self.other_chunk_size, g2), (self.other_chunk_size, g1),
+                      (self.other_chunk_size, g1), (1, g2))
+        for cnt, sz in counts:
             out.append((o, cnt, sz))
             o += cnt * sz
         return out
@@ -607,12 +613,46 @@ def iter_chunk(params: Phase1Parameters):
     return out
 
 
+def phase1_computation_marlin(params: Phase1Parameters, inp: bytes, compressed_in, compressed_out, check_in,
+                              tau: int, alpha: int) -> bytearray:
+    """Phase1::computation, Marlin branch (phase1/src/computation.rs:195-302)."""
+    cv, r = params.curve, params.curve.r
+    k, N = params.total_size_in_log2, params.powers_length
+    out = bytearray(params.get_length(compressed_out))
+    si, so = params.split_offsets(compressed_in), params.split_offsets(compressed_out)
+    views = [inp[o:o + c * s] for (o, c, s) in si]
+
+    def put(vec, start, data):
+        o, _, s = so[vec]
+        out[o + start * s:o + start * s + len(data)] = data
+
+    if params.chunk_index == 0:
+        dbp = [pow(tau, N - 1 - (1 << i) + 2, r) for i in range(k)]
+        g2_inv = [pow(x, -1, r) for x in dbp]
+        put(1, 2, apply_powers(cv.g2, views[1], compressed_in, check_in, compressed_out, 2, k + 2, g2_inv))
+        g1_deg = []
+        for f in dbp:
+            g1_deg += [f, f * tau % r, f * tau * tau % r]
+        put(2, 3, apply_powers(cv.g1, views[2], compressed_in, check_in, compressed_out, 3, 3 + 3 * k, g1_deg, alpha))
+        put(2, 0, apply_powers(cv.g1, views[2], compressed_in, check_in, compressed_out, 0, 3,
+                               generate_powers_of_tau(cv, tau, 0, 3), alpha))
+        put(1, 0, apply_powers(cv.g2, views[1], compressed_in, check_in, compressed_out, 0, 2,
+                               generate_powers_of_tau(cv, tau, 0, 2)))
+    off = params.chunk_index * params.chunk_size if params.contribution_mode == CHUNKED_MODE else 0
+    for (start, end) in iter_chunk(params):
+        powers = generate_powers_of_tau(cv, tau, start, end)
+        put(0, start - off, apply_powers(cv.g1, views[0], compressed_in, check_in, compressed_out, start - off, end - off, powers))
+    return out
+
+
 def phase1_computation(params: Phase1Parameters, inp: bytes, compressed_in, compressed_out, check_in,
                        tau: int, alpha: int, beta: int) -> bytearray:
     """Phase1::computation, Groth16 branch (phase1/src/computation.rs:16-193).
 
     Returns a buffer of params.get_length(compressed_out) bytes whose first 64 bytes (hash) are left zero:
     the caller writes the hash (phase1-cli/src/contribute.rs:92-96)."""
+    if params.proving_system == MARLIN:
+        return phase1_computation_marlin(params, inp, compressed_in, compressed_out, check_in, tau, alpha)
     cv = params.curve
     out = bytearray(params.get_length(compressed_out))
     si = params.split_offsets(compressed_in)

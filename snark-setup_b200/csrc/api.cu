@@ -296,6 +296,7 @@ struct VectorJob {
     const uint32_t* d_coeff_m;
     int has_coeff;
     const char* what;
+    bool exps_on_device = false;  // `exps` already lives in device memory even when in/out are host buffers
 };
 
 int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_stream) {
@@ -306,7 +307,8 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
     const size_t ntiles = (j.n + T - 1) / T;
     const int nl = (host && ntiles > 1) ? 2 : 1;
     size_t per_lane = scratch_bytes(o, T) + 256;
-    if (host) per_lane += align_up(isz * T, 256) + align_up(osz * T, 256) + (j.exps ? align_up((size_t)o.fr_bytes * T, 256) : 0);
+    const bool stage_exps = host && j.exps && !j.exps_on_device;
+    if (host) per_lane += align_up(isz * T, 256) + align_up(osz * T, 256) + (stage_exps ? align_up((size_t)o.fr_bytes * T, 256) : 0);
     LaneGuard lg[2];
     for (int k = 0; k < nl; k++) {
         int rc = lane_acquire(device, per_lane + ntiles * 8 + 256, &lg[k].l);
@@ -341,10 +343,12 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
             uint8_t* bi = cv.take<uint8_t>(isz * T);
             uint8_t* bo = cv.take<uint8_t>(osz * T);
             CU(cudaMemcpyAsync(bi, j.in + e0 * isz, cnt * isz, cudaMemcpyHostToDevice, s));
-            if (j.exps) {
+            if (stage_exps) {
                 uint8_t* be = cv.take<uint8_t>((size_t)o.fr_bytes * T);
                 CU(cudaMemcpyAsync(be, j.exps + e0 * o.fr_bytes, cnt * o.fr_bytes, cudaMemcpyHostToDevice, s));
                 d_exps = be;
+            } else if (j.exps) {
+                d_exps = j.exps + e0 * o.fr_bytes;
             }
             d_in = bi;
             d_out = bo;
@@ -482,18 +486,66 @@ int phase1_sizes(const ss_phase1_params* p, ss_phase1_sizes* o) {
     return SS_OK;
 }
 
+// Phase1::computation, Marlin branch (phase1/src/computation.rs:195-302): tau_g1 over the chunk's powers as in
+// Groth16; on chunk 0 additionally the k+2 tau_g2 and 3+3k alpha_g1 elements, whose scalars (inverse degree-bound
+// powers etc.) are produced by k_marlin_scalars and applied through the explicit-exponent path.
+int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& z, const GroupOps& g1, const GroupOps& g2,
+                              const uint8_t* input, size_t input_len, uint8_t* output, size_t output_len, int cin, int cout,
+                              int check, const uint8_t* tau, const uint8_t* alpha, bool host, cudaStream_t user_stream) {
+    const uint64_t need_in = cin ? z.contribution_size - z.public_key_size : z.accumulator_size;
+    const uint64_t need_out = cout ? z.contribution_size - z.public_key_size : z.accumulator_size;
+    if (input_len < need_in) return fail(SS_ERR_INVALID_LENGTH, 0, need_in, input_len, "input buffer too short");
+    if (output_len < need_out) return fail(SS_ERR_INVALID_LENGTH, 0, need_out, output_len, "output buffer too short");
+    for (const uint8_t* s : {tau, alpha})
+        if (!scalar_is_canonical(p->curve, s)) return fail(SS_ERR_INVALID_DATA, 0, 0, 0, "scalar >= r");
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int device = g_devices[0];
+    CU(cudaSetDevice(device));
+    const uint64_t k = p->total_size_in_log2;
+    const bool chunk0 = p->chunk_index == 0 || p->contribution_mode == SS_MODE_FULL;
+    const uint64_t n_g2 = chunk0 ? k + 2 : 0, n_al = chunk0 ? 3 + 3 * k : 0;
+    auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
+    LaneGuard lane;
+    if ((rc = lane_acquire(device, 4096 + (n_g2 + n_al) * g1.fr_bytes, &lane.l))) return rc;
+    ScalarSetup sc;
+    const uint8_t* coeffs[3] = {nullptr, alpha, nullptr};
+    if ((rc = sc.init(g1, tau, coeffs, lane.l->stream))) return rc;
+    const uint64_t first = p->contribution_mode == SS_MODE_CHUNKED ? p->chunk_index * p->chunk_size : 0;
+    const uint64_t n1 = z.g1_chunk_size;
+    VectorJob jt = {&g1, input + 64, output + 64, cin, cout, check, n1, nullptr, sc.d_tab, first, sc.d_coeff_m[0], 0, "tau_g1"};
+    if ((rc = run_vector_on(device, jt, host, user_stream))) return rc;
+    if (!chunk0) return SS_OK;
+    uint8_t* d_g2s = lane.l->buf;
+    uint8_t* d_als = d_g2s + align_up(n_g2 * g1.fr_bytes, 256);
+    g1.marlin_scalars(sc.d_tab, z.powers_length, (int)k, reinterpret_cast<uint32_t*>(d_g2s), reinterpret_cast<uint32_t*>(d_als),
+                      lane.l->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(lane.l->stream));
+    const uint64_t oi2 = 64 + n1 * sz(g1, cin), oo2 = 64 + n1 * sz(g1, cout);
+    VectorJob j2 = {&g2, input + oi2, output + oo2, cin, cout, check, n_g2, d_g2s, sc.d_tab, 0, sc.d_coeff_m[0], 0, "tau_g2"};
+    j2.exps_on_device = true;
+    if ((rc = run_vector_on(device, j2, host, user_stream))) return rc;
+    const uint64_t oi3 = oi2 + n_g2 * sz(g2, cin), oo3 = oo2 + n_g2 * sz(g2, cout);
+    VectorJob j3 = {&g1, input + oi3, output + oo3, cin, cout, check, n_al, d_als, sc.d_tab, 0, sc.d_coeff_m[1], 1, "alpha_g1"};
+    j3.exps_on_device = true;
+    return run_vector_on(device, j3, host, user_stream);
+}
+
 int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
                             size_t output_len, int cin, int cout, int check, const uint8_t* tau,
                             const uint8_t* alpha, const uint8_t* beta, bool host, cudaStream_t user_stream) {
-    if (!p || !input || !output || !tau || !alpha || !beta) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (!p || !input || !output || !tau || !alpha || (!beta && p->proving_system != SS_MARLIN))
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
     if (check < 0 || check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode %d", check);
-    if (p->proving_system != SS_GROTH16)
-        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "only the Groth16 accumulator layout is implemented");
     ss_phase1_sizes z;
     int rc = phase1_sizes(p, &z);
     if (rc) return rc;
     const GroupOps& g1 = *group_ops(p->curve, SS_G1);
     const GroupOps& g2 = *group_ops(p->curve, SS_G2);
+    if (p->proving_system == SS_MARLIN)
+        return phase1_computation_marlin(p, z, g1, g2, input, input_len, output, output_len, cin, cout, check, tau, alpha, host,
+                                         user_stream);
     const uint64_t need_in = cin ? z.contribution_size - z.public_key_size : z.accumulator_size;
     const uint64_t need_out = cout ? z.contribution_size - z.public_key_size : z.accumulator_size;
     if (input_len < need_in) return fail(SS_ERR_INVALID_LENGTH, 0, need_in, input_len, "input buffer too short");

@@ -311,7 +311,8 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
                                     int compressed_new_challenge, int subgroup_mode, int ratio_check,
                                     const uint8_t* rho_seed, uint8_t* pairs, bool host, cudaStream_t stream) {
     if (!p || !output) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
-    if (p->proving_system != SS_GROTH16) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "only Groth16 layout is implemented");
+    if (p->proving_system != SS_GROTH16 && p->proving_system != SS_MARLIN)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown proving system %d", p->proving_system);
     if (ratio_check && (!rho_seed || !pairs)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "ratio check needs rho_seed and pairs");
     ss_phase1_sizes z;
     int rc = phase1_sizes(p, &z);
@@ -325,7 +326,14 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
     if ((rc = ensure_init())) return rc;
     auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
     const uint64_t n1 = z.g1_chunk_size, n2 = z.other_chunk_size;
-    const uint64_t cnt[5] = {n1, n2, n2, n2, 1};
+    // Marlin (verification.rs:413-483): tau_g1 over the chunk, plus k+2 tau_g2 and 3+3k alpha_g1 elements on chunk 0;
+    // only tau_g1 is a power sequence (its ratio is what aggregate_verification checks, :649-672)
+    const bool marlin = p->proving_system == SS_MARLIN;
+    const bool chunk0 = p->chunk_index == 0 || p->contribution_mode == SS_MODE_FULL;
+    const uint64_t mk = p->total_size_in_log2;
+    const uint64_t cnt[5] = {n1, marlin ? (chunk0 ? mk + 2 : 0) : n2, marlin ? (chunk0 ? 3 + 3 * mk : 0) : n2, marlin ? 0 : n2,
+                             marlin ? 0u : 1u};
+    const bool has_ratio[5] = {true, !marlin, !marlin, !marlin, false};
     const GroupOps* gs[5] = {&g1, &g2, &g1, &g1, &g2};
     const int grp[5] = {SS_G1, SS_G2, SS_G1, SS_G1, SS_G2};
     const char* names[5] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1", "beta_g2"};
@@ -343,7 +351,7 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
     }
     for (int v = 0; v < 4; v++)
         // a vector of one element cannot be ratio-checked (verification.rs:238-241 -> BatchTooSmall)
-        if (ratio_check && cnt[v] == 1) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: batch too small", names[v]);
+        if (ratio_check && has_ratio[v] && cnt[v] == 1) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: batch too small", names[v]);
 
     // One worker per device: device d takes the d-th contiguous part of every vector (plus one element of
     // overlap for the ratio pairs, helpers.rs:388-390) and produces partial (s, sx); rho_i is indexed by
@@ -371,8 +379,9 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
             const uint64_t s0 = di * base + std::min<uint64_t>(di, rem), e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
             if (e0 == s0) return SS_OK;
             const bool last = e0 == cnt[v];
-            const uint64_t nread = (e0 - s0) + ((ratio_check && !last) ? 1 : 0);
-            const bool do_ratio = ratio_check && nread >= 2;
+            const bool want_ratio = ratio_check && has_ratio[v];
+            const uint64_t nread = (e0 - s0) + ((want_ratio && !last) ? 1 : 0);
+            const bool do_ratio = want_ratio && nread >= 2;
             uint8_t* ps = partial[di].data() + op[v];
             RatioJob j = {p->curve, grp[v], output + oa[v] + s0 * sz(*gs[v], compressed_output), nullptr, compressed_output,
                           SS_CHECK_ONLY_NON_ZERO, nread, subgroup_mode != SS_SUBGROUP_NO, do_ratio, nullptr, rho_seed,

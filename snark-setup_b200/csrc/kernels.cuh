@@ -143,6 +143,42 @@ SS_D void store_affine(uint32_t* aff, uint64_t i, const Affine<typename G::F>& p
     for (int k = 0; k < W2 / 4; k++) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
 }
 
+// Marlin's short scalar vectors (phase1/src/computation.rs:198-257), canonical LE, one thread per degree bound i:
+//   dbp_i = tau^(N - 1 - 2^i + 2);  tau_g2[2+i] <- 1/dbp_i;  alpha_g1[3+3i .. 3+3i+3) <- dbp_i * {1, tau, tau^2}
+// and the fixed heads tau_g2[0..2) <- {1, tau}, alpha_g1[0..3) <- {1, tau, tau^2} (alpha is applied as `coeff`).
+template <class FrP>
+__global__ void k_marlin_scalars(const uint32_t* __restrict__ tab, uint64_t powers_length, int k, uint32_t* out_g2,
+                                 uint32_t* out_alpha) {
+    constexpr int N = FrP::N;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > k) return;
+    Fp<FrP> tau, tau2;
+#pragma unroll
+    for (int w = 0; w < N; w++) {
+        tau.l[w] = __ldg(tab + w);
+        tau2.l[w] = __ldg(tab + N + w);
+    }
+    auto put = [&](uint32_t* dst, int slot, const Fp<FrP>& m) {
+        Fp<FrP> c = fp_from_mont(m);
+#pragma unroll
+        for (int w = 0; w < N; w++) dst[slot * N + w] = c.l[w];
+    };
+    if (i == k) {  // heads
+        put(out_g2, 0, Fp<FrP>::one());
+        put(out_g2, 1, tau);
+        put(out_alpha, 0, Fp<FrP>::one());
+        put(out_alpha, 1, tau);
+        put(out_alpha, 2, tau2);
+        return;
+    }
+    Fp<FrP> dbp = tau_power<FrP>(tab, powers_length - 1 - (1ull << i) + 2);
+    put(out_g2, 2 + i, fp_inv(dbp));
+    put(out_alpha, 3 + 3 * i, dbp);
+    Fp<FrP> t = fp_mul(dbp, tau);
+    put(out_alpha, 3 + 3 * i + 1, t);
+    put(out_alpha, 3 + 3 * i + 2, fp_mul(dbp, tau2));
+}
+
 // ---- stage 1: read_batch ------------------------------------------------------------------------
 // Affine scratch `aff`: [n][2*FW] words (x then y, Montgomery) + one flag byte per element
 // (1 = point at infinity).
@@ -385,6 +421,7 @@ struct GroupOps {
     void (*prepare_scalars)(const uint32_t* tau_le, const uint32_t* coeff_le, uint32_t* tab, uint32_t* coeff_m,
                             cudaStream_t);
     void (*powers)(const uint32_t* tab, uint64_t start, uint64_t n, uint32_t* out, cudaStream_t);
+    void (*marlin_scalars)(const uint32_t* tab, uint64_t powers_length, int k, uint32_t* out_g2, uint32_t* out_alpha, cudaStream_t);
     void (*decode)(const DecodeArgs&, cudaStream_t);
     void (*scalar_mul)(const ScalarMulArgs&, cudaStream_t);
     void (*normalize_encode)(const NormalizeArgs&, cudaStream_t);
@@ -403,6 +440,10 @@ struct GroupLaunch {
     static void powers(const uint32_t* tab, uint64_t start, uint64_t n, uint32_t* out, cudaStream_t s) {
         if (!n) return;
         k_powers<FrP><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(tab, start, n, out);
+    }
+    static void marlin_scalars(const uint32_t* tab, uint64_t powers_length, int k, uint32_t* out_g2, uint32_t* out_alpha,
+                               cudaStream_t s) {
+        k_marlin_scalars<FrP><<<(k + 1 + 31) / 32, 32, 0, s>>>(tab, powers_length, k, out_g2, out_alpha);
     }
     static void scalar_mul(const ScalarMulArgs& a, cudaStream_t s) {
         if (!a.n) return;
@@ -437,6 +478,7 @@ struct GroupLaunch {
         o.coord_words = FieldWords<typename G::F>::W;
         o.prepare_scalars = &prepare_scalars;
         o.powers = &powers;
+        o.marlin_scalars = &marlin_scalars;
         o.scalar_mul = &scalar_mul;
         o.normalize_encode = &normalize_encode;
         o.decode = &decode;

@@ -168,3 +168,30 @@ def test_phase1_computation_chunked_mode(chunk_index):
     out = bytearray(sp.get_length(True))
     S.phase1_computation(sp, bytes(acc), out, False, True, S.CHECK_NO, tau, alpha, beta)
     assert bytes(out) == bytes(want)
+
+
+@pytest.mark.parametrize("mode,chunk_index,chunk_size", [(0, 0, 0), (1, 0, 4), (1, 1, 4)])
+def test_phase1_marlin(mode, chunk_index, chunk_size):
+    """ProvingSystem::Marlin (phase1/src/computation.rs:195-302): tau_g1 over 2^k powers, and on chunk 0 the
+    k+2 tau_g2 elements with inverse degree-bound powers and the 3+3k alpha_g1 elements."""
+    cv = R.BLS12_377
+    power, batch = 3, 8
+    rng = random.Random(900 + chunk_index)
+    rp = R.Phase1Parameters(cv, power, batch, mode, chunk_index, chunk_size, R.MARLIN)
+    sp = S.Phase1Parameters(S.BLS12_377, power, batch, mode, chunk_index, chunk_size, 1)
+    assert (sp.accumulator_size, sp.contribution_size) == (rp.accumulator_size, rp.contribution_size)
+    tau, alpha = rng.randrange(2, cv.r), rng.randrange(2, cv.r)
+    acc = bytearray(rp.get_length(False))
+    for vec, (o, c, s) in enumerate(rp.split_offsets(False)):
+        g = cv.g2 if vec in (1, 4) else cv.g1
+        acc[o:o + c * s] = g.write_batch([g.mul(g.gen, rng.randrange(1, cv.r)) for _ in range(c)], False)
+    for cout in (False, True):
+        want = R.phase1_computation(rp, bytes(acc), False, cout, R.NO, tau, alpha, 0)
+        out = bytearray(sp.get_length(cout))
+        S.phase1_computation(sp, bytes(acc), out, False, cout, S.CHECK_NO, tau, alpha, 1)
+        assert bytes(out) == bytes(want), cout
+    # verification loop: nonzero + subgroup checks and re-emit of every Marlin vector; tau_g1 ratio pair
+    resp = bytes(R.phase1_computation(rp, bytes(acc), False, True, R.NO, tau, alpha, 0))
+    newc = bytearray(sp.get_length(False))
+    S.phase1_verification_vectors(sp, resp, True, newc, False, ratio_check=False)
+    assert bytes(newc[64:]) == bytes(R.phase1_computation(rp, bytes(acc), False, False, R.NO, tau, alpha, 0))[64:]
