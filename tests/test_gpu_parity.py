@@ -195,3 +195,36 @@ def test_phase1_marlin(mode, chunk_index, chunk_size):
     newc = bytearray(sp.get_length(False))
     S.phase1_verification_vectors(sp, resp, True, newc, False, ratio_check=False)
     assert bytes(newc[64:]) == bytes(R.phase1_computation(rp, bytes(acc), False, False, R.NO, tau, alpha, 0))[64:]
+
+
+def test_config_c1_bls12_377_power10_batch256():
+    """BASELINE.json configs[0]: new + contribute + verify at power 10, batch 256 — the whole response and the
+    whole new challenge byte for byte against the C++ oracle, plus the BLAKE2b-512 digests a CLI run would
+    write to the .hash files (phase1-cli/src/contribute.rs:143-151)."""
+    import hashlib
+    import coracle as O
+    cv, cid = R.BLS12_377, S.BLS12_377
+    rp = R.Phase1Parameters(cv, 10, 256)
+    sp = S.Phase1Parameters(cid, 10, 256)
+    assert (sp.accumulator_size, sp.contribution_size) == (589984, 295600)
+    assert len(sp.iter_chunk()) == 9
+    rng = random.Random(1010)
+    k0 = [rng.randrange(2, cv.r) for _ in range(3)]
+    k1 = [rng.randrange(2, cv.r) for _ in range(3)]
+    blank = bytes(R.phase1_initialization(rp, False))
+    args = (rp.g1_chunk_size, rp.other_chunk_size, 0)
+    chal_o = O.phase1_computation(0, blank, rp.get_length(False), False, False, 3, *args, *k0)
+    chal = bytearray(sp.get_length(False))
+    S.phase1_computation(sp, blank, chal, False, False, S.CHECK_NO, *k0)
+    assert bytes(chal) == chal_o
+    resp_o = O.phase1_computation(0, chal_o, rp.get_length(True), False, True, 3, *args, *k1)
+    resp = bytearray(sp.get_length(True))
+    S.phase1_computation(sp, bytes(chal), resp, False, True, S.CHECK_NO, *k1)
+    assert hashlib.blake2b(bytes(resp)).digest() == hashlib.blake2b(resp_o).digest()
+    newc_o = O.phase1_computation(0, chal_o, rp.get_length(False), False, False, 3, *args, *k1)
+    newc = bytearray(sp.get_length(False))
+    pairs = S.phase1_verification_vectors(sp, bytes(resp), True, newc, False, seed=bytes(range(32)))
+    assert hashlib.blake2b(bytes(newc)).digest() == hashlib.blake2b(newc_o).digest()
+    tau = k0[0] * k1[0] % cv.r
+    for (s, sx), grp in zip(pairs, (0, 1, 0, 0)):
+        assert O.apply_powers(0, grp, s, False, 3, False, 1, powers=[tau]) == sx
