@@ -7,7 +7,8 @@
 //   Phase1::computation (Groth16)         phase1/src/computation.rs:40-193
 // The reference walks each vector in `batch_size` windows on rayon threads; results do not depend
 // on the windowing, so here each vector is cut into device tiles (default 2^18 elements) that are
-// pipelined over two CUDA streams: H2D of tile k+1 overlaps the kernels of tile k.
+// pipelined over two CUDA streams (H2D of tile k+1 overlaps the kernels of tile k), the five vectors
+// of a call run on concurrent lanes, and with several devices every vector is split D ways.
 #ifndef __CUDACC__
 #error "api.cu is the CUDA product path and must be built with nvcc (no CPU fallback exists)"
 #endif
@@ -275,12 +276,6 @@ uint32_t normalize_threads(uint64_t n) {
     if (t < 1024) t = std::min<uint64_t>(n, 1024);
     return (uint32_t)t;
 }
-
-// ---- scalar set-up shared by the vectors of one call ----------------------------------------------
-struct ScalarCtx {
-    uint32_t* d_tab = nullptr;      // [64][frw]
-    uint32_t* d_coeff[3] = {};      // Montgomery coefficients (slot 0 = "one")
-};
 
 // One vector of `n` elements.  host==true: in/out are host pointers and are staged tile by tile;
 // host==false: in/out are device pointers of `device`.
