@@ -52,6 +52,21 @@ struct Fp {
     SS_HD bool operator!=(const Fp& o) const { return !(*this == o); }
 };
 
+// -x computed as (x ^ 0xffffffff) + 1 with the mask read from constant memory: when ptxas can prove that a
+// multiplier operand is a negation it folds the sign into the low product and stops fusing the
+// mad.lo/madc.hi pairs into IMAD.WIDE (144 instead of 267 fused products per 12-limb multiplication).
+#if defined(__CUDACC__)
+static __device__ __constant__ uint32_t kOpaqueOnes = 0xffffffffu;
+#else
+static const uint32_t kOpaqueOnes = 0xffffffffu;
+#endif
+SS_HD uint32_t opaque_neg(uint32_t x) { return (x ^ kOpaqueOnes) + 1u; }
+#if defined(SS_NO_P0_TRICK)  // A/B switch
+#define SS_P0_TRICK false
+#else
+#define SS_P0_TRICK true
+#endif
+
 // r = (a >= p) ? a - p : a      (a < 2p)
 template <class P>
 SS_HD void fp_final_sub(uint32_t* a) {
@@ -118,7 +133,10 @@ SS_HD Fp<P> fp_dbl(const Fp<P>& a) {
 template <class P>
 SS_HD void mont_reduce_step(uint32_t* X, uint32_t* Y) {
     constexpr int N = P::N;
-    uint32_t m = mul_lo(X[0], P::inv());
+    // p = 1 mod 2^32 (both BLS12-377 moduli): -p^-1 = -1, so m = -X[0] and the limb-0 product m*p[0] = m
+    // only turns X[0] into 0 with carry (X[0] != 0) — no multiplier instruction for either.
+    constexpr bool P0_ONE = SS_P0_TRICK && (P::mod(0) == 1u);
+    uint32_t m = P0_ONE ? opaque_neg(X[0]) : mul_lo(X[0], P::inv());
     // odd limbs of p into Y
     Y[0] = mad_lo_cc(P::mod(1), m, Y[0]);
     Y[1] = madc_hi_cc(P::mod(1), m, Y[1]);
@@ -130,8 +148,13 @@ SS_HD void mont_reduce_step(uint32_t* X, uint32_t* Y) {
     Y[N - 2] = madc_lo_cc(P::mod(N - 1), m, Y[N - 2]);
     Y[N - 1] = madc_hi(P::mod(N - 1), m, Y[N - 1]);
     // even limbs of p into X
-    X[0] = mad_lo_cc(P::mod(0), m, X[0]);
-    X[1] = madc_hi_cc(P::mod(0), m, X[1]);
+    if (P0_ONE) {
+        X[0] = add_cc(X[0], m);
+        X[1] = addc_cc(X[1], 0);
+    } else {
+        X[0] = mad_lo_cc(P::mod(0), m, X[0]);
+        X[1] = madc_hi_cc(P::mod(0), m, X[1]);
+    }
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
         X[j] = madc_lo_cc(P::mod(j), m, X[j]);
@@ -193,6 +216,73 @@ SS_HD Fp<P> fp_mul_inl(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// ---- dedicated squaring --------------------------------------------------------------------------
+// a^2 = 2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum_i a_i^2 2^(64 i): N(N+1)/2 wide products instead of N^2,
+// followed by a separate Montgomery reduction of the 2N-limb square (N^2 wide products): 222 instead
+// of 288 IMAD.WIDE for N = 12.  Off-diagonal products are accumulated in two 2N-limb arrays so that
+// every product again lands on an aligned register pair: E[k] sits at limb position k and takes the
+// products with even i+j, O[k] sits at position k+1 and takes the odd ones.  Rows are processed in
+// increasing i, so the limb after the end of each chain has only ever received carry bits and one
+// `addc` closes the chain.
+
+// reduction iteration with the >>32 folded into the odd chain (mont_step with a := p, b_i := m)
+template <class P>
+SS_HD void mont_redc_shift_step(uint32_t* X /*old Y*/, uint32_t* Y /*old X*/) {
+    constexpr int N = P::N;
+    constexpr bool P0_ONE = SS_P0_TRICK && (P::mod(0) == 1u);  // see mont_reduce_step
+    uint32_t m = P0_ONE ? opaque_neg(X[0] + Y[1]) : mul_lo(X[0] + Y[1], P::inv());
+    X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        Y[j] = madc_lo_cc(P::mod(j + 1), m, Y[j + 2]);
+        Y[j + 1] = madc_hi_cc(P::mod(j + 1), m, Y[j + 3]);
+    }
+    Y[N - 2] = madc_lo_cc(P::mod(N - 1), m, 0);
+    Y[N - 1] = madc_hi(P::mod(N - 1), m, 0);
+    if (P0_ONE) {
+        X[0] = add_cc(X[0], m);
+        X[1] = addc_cc(X[1], 0);
+    } else {
+        X[0] = mad_lo_cc(P::mod(0), m, X[0]);
+        X[1] = madc_hi_cc(P::mod(0), m, X[1]);
+    }
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(P::mod(j), m, X[j]);
+        X[j + 1] = madc_hi_cc(P::mod(j), m, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0);
+}
+
+// Montgomery reduction of a 2N-limb value T < p * 2^(32N) (consumed in place): T / 2^(32N) mod p
+template <class P>
+SS_HD Fp<P> mont_redc_wide(uint32_t* E) {
+    constexpr int N = P::N;
+    // X aligned at 0 = T[0..N), Y = 0
+    uint32_t* X = E;  // low half is consumed in place
+    uint32_t Y[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) Y[k] = 0;
+    mont_reduce_step<P>(X, Y);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_redc_shift_step<P>(Y, X);
+        if (i + 1 < N) mont_redc_shift_step<P>(X, Y);
+    }
+    // W = Yrole + (Xrole >> 32) with Xrole = Y, Yrole = X (odd number of swaps), then + T_hi
+    Fp<P> r;
+    r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(X[j], Y[j + 1]);
+    r.l[N - 1] = addc(X[N - 1], 0);
+    r.l[0] = add_cc(r.l[0], E[N]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(r.l[j], E[N + j]);
+    r.l[N - 1] = addc(r.l[N - 1], E[2 * N - 1]);
+    fp_final_sub<P>(r.l);
+    return r;
+}
+
 // By default the multiplier is ONE out-of-line function per field and kernel: operands travel in
 // registers (no local memory), the call costs ~50 MOVs that issue in the shadow of the IMAD pipe,
 // and kernels stay a few thousand instructions long instead of hundreds of KB of inlined
@@ -211,38 +301,6 @@ SS_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #else
     return fp_mul_inl(a, b);
 #endif
-}
-
-// ---- dedicated squaring --------------------------------------------------------------------------
-// a^2 = 2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum_i a_i^2 2^(64 i): N(N+1)/2 wide products instead of N^2,
-// followed by a separate Montgomery reduction of the 2N-limb square (N^2 wide products): 222 instead
-// of 288 IMAD.WIDE for N = 12.  Off-diagonal products are accumulated in two 2N-limb arrays so that
-// every product again lands on an aligned register pair: E[k] sits at limb position k and takes the
-// products with even i+j, O[k] sits at position k+1 and takes the odd ones.  Rows are processed in
-// increasing i, so the limb after the end of each chain has only ever received carry bits and one
-// `addc` closes the chain.
-
-// reduction iteration with the >>32 folded into the odd chain (mont_step with a := p, b_i := m)
-template <class P>
-SS_HD void mont_redc_shift_step(uint32_t* X /*old Y*/, uint32_t* Y /*old X*/) {
-    constexpr int N = P::N;
-    uint32_t m = mul_lo(X[0] + Y[1], P::inv());
-    X[0] = add_cc(X[0], Y[1]);
-#pragma unroll
-    for (int j = 0; j < N - 2; j += 2) {
-        Y[j] = madc_lo_cc(P::mod(j + 1), m, Y[j + 2]);
-        Y[j + 1] = madc_hi_cc(P::mod(j + 1), m, Y[j + 3]);
-    }
-    Y[N - 2] = madc_lo_cc(P::mod(N - 1), m, 0);
-    Y[N - 1] = madc_hi(P::mod(N - 1), m, 0);
-    X[0] = mad_lo_cc(P::mod(0), m, X[0]);
-    X[1] = madc_hi_cc(P::mod(0), m, X[1]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-        X[j] = madc_lo_cc(P::mod(j), m, X[j]);
-        X[j + 1] = madc_hi_cc(P::mod(j), m, X[j + 1]);
-    }
-    Y[N - 1] = addc(Y[N - 1], 0);
 }
 
 template <class P>
@@ -299,29 +357,7 @@ SS_HD Fp<P> fp_sqr_inl(const Fp<P>& av) {
     }
     E[2 * N - 2] = madc_lo_cc(a[N - 1], a[N - 1], E[2 * N - 2]);
     E[2 * N - 1] = madc_hi(a[N - 1], a[N - 1], E[2 * N - 1]);
-    // Montgomery reduction of T_lo; X aligned at 0 = T[0..N), Y = 0
-    uint32_t* X = E;  // low half is consumed in place
-    uint32_t Y[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) Y[k] = 0;
-    mont_reduce_step<P>(X, Y);
-#pragma unroll
-    for (int i = 1; i < N; i += 2) {
-        mont_redc_shift_step<P>(Y, X);
-        if (i + 1 < N) mont_redc_shift_step<P>(X, Y);
-    }
-    // W = Yrole + (Xrole >> 32) with Xrole = Y, Yrole = X (odd number of swaps), then + T_hi
-    Fp<P> r;
-    r.l[0] = add_cc(X[0], Y[1]);
-#pragma unroll
-    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(X[j], Y[j + 1]);
-    r.l[N - 1] = addc(X[N - 1], 0);
-    r.l[0] = add_cc(r.l[0], E[N]);
-#pragma unroll
-    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(r.l[j], E[N + j]);
-    r.l[N - 1] = addc(r.l[N - 1], E[2 * N - 1]);
-    fp_final_sub<P>(r.l);
-    return r;
+    return mont_redc_wide<P>(E);
 }
 
 #if defined(__CUDACC__)

@@ -117,6 +117,17 @@ __global__ void k_fpmul(uint32_t* out, int iters, uint32_t seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+template <class P>
+__global__ void k_fpsqr(uint32_t* out, int iters, uint32_t seed) {
+    Fp<P> x;
+    for (int i = 0; i < P::N; i++) x.l[i] = seed + threadIdx.x * 31 + i;
+    x.l[P::N - 1] = 0;
+    for (int it = 0; it < iters; it++) x = fp_sqr(x);
+    uint32_t r = 0;
+    for (int i = 0; i < P::N; i++) r ^= x.l[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 // two independent multiplications per iteration (ILP 2)
 template <class P>
 __global__ void k_fpmul2(uint32_t* out, int iters, uint32_t seed) {
@@ -174,7 +185,7 @@ int main() {
                (double)blocks * tpb * iters * 8 / t * 1e-9, (double)blocks * tpb * iters * 4 / t * 1e-9);
     }
     CK(cudaGetLastError());
-#ifdef SS_MUL_INLINE
+#if defined(SS_MUL_INLINE)
     const char* mode = "inline";
 #else
     const char* mode = "call";
@@ -187,6 +198,8 @@ int main() {
         printf("{\"bench\": \"fp_mul\", \"mode\": \"%s\", \"limbs\": 8, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", mode, warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
         t = time_kernel([&] { k_fpmul<Bls377Fq><<<blocks, tpb>>>(out, it, 7); }, 3);
         printf("{\"bench\": \"fp_mul\", \"mode\": \"%s\", \"limbs\": 12, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", mode, warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
+        t = time_kernel([&] { k_fpsqr<Bls377Fq><<<blocks, tpb>>>(out, it, 7); }, 3);
+        printf("{\"bench\": \"fp_sqr\", \"mode\": \"%s\", \"limbs\": 12, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", mode, warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
         t = time_kernel([&] { k_fpmul<Bls377FqSplit><<<blocks, tpb>>>(out, it, 7); }, 3);
         printf("{\"bench\": \"fp_mul_split_mp\", \"limbs\": 12, \"warps_per_sm\": %d, \"gmul_s\": %.2f}\n", warps_per_sm, (double)blocks * tpb * it / t * 1e-9);
         t = time_kernel([&] { k_fpmul2<Bls377Fq><<<blocks, tpb>>>(out, it, 7); }, 3);
