@@ -235,6 +235,34 @@ int ss_phase1_verification_vectors_dev(const ss_phase1_params* p, const void* d_
                                        int compressed_new_challenge, int subgroup_mode, int ratio_check,
                                        const uint8_t* rho_seed, uint8_t* pairs, void* stream);
 
+/* -------------------------------------------------------------------------------------------- */
+/* prepare_phase2: powers of tau -> Lagrange coefficients                */
+/* -------------------------------------------------------------------------------------------- */
+/* to_coeffs — setup-utils/src/groth16_utils.rs:44-53: `domain.ifft` over the group followed by
+ * normalize_batch, on n serialized elements (n a power of two, the radix-2 domain of that size):
+ *   out_j = (1/n) * sum_i w^(-i*j) * in_i,   w = Fr::get_root_of_unity(n)
+ * (ark-ff 0.4: TWO_ADIC_ROOT_OF_UNITY = GENERATOR^((r-1)/2^s) squared down to order n). */
+int ss_group_ifft(int curve, int group, const uint8_t* in, int in_compressed, int check, size_t n, uint8_t* out,
+                  int out_compressed);
+
+/* h_query_groth16 — setup-utils/src/groth16_utils.rs:59-63: out_i = powers[i + degree] - powers[i] for
+ * i < degree - 1 (G1).  n_powers < 2*degree - 1 => SS_ERR_INVALID_LENGTH (the reference panics). */
+int ss_h_query_groth16(int curve, const uint8_t* powers, int in_compressed, int check, size_t n_powers, size_t degree,
+                       uint8_t* out, int out_compressed);
+
+/* domain_size (groth16_utils.rs:65-69) and the byte length Groth16Params::write produces
+ * (groth16_utils.rs:134-168): alpha_g1, beta_g1, beta_g2, coeffs_g1[m], coeffs_g2[m],
+ * alpha_coeffs_g1[m], beta_coeffs_g1[m], h_g1[m-1]. */
+int ss_groth16_params_size(int curve, uint64_t phase2_size, int compressed, uint64_t* domain_size, size_t* bytes);
+
+/* Groth16Params::new + ::write — setup-utils/src/groth16_utils.rs:81-131,134-168, the body of
+ * prepare_phase2 (phase2-cli/src/prepare_phase2.rs:16-70): `accumulator` is a full-mode Groth16 phase-1
+ * accumulator (64-byte hash prefix included, as Phase1::deserialize takes it); elements are read with
+ * `check`.  A domain larger than the accumulator's powers => SS_ERR_INVALID_LENGTH (reference: slice panic). */
+int ss_groth16_params_new(const ss_phase1_params* p, const uint8_t* accumulator, size_t accumulator_len,
+                          int compressed_input, int check, uint64_t phase2_size, uint8_t* out, size_t out_len,
+                          int compressed_output);
+
 #ifdef __cplusplus
 }
 #endif

@@ -692,3 +692,129 @@ def phase1_initialization(params: Phase1Parameters, compressed) -> bytearray:
         g = cv.g2 if vec in (1, 4) else cv.g1
         out[o:o + c * s] = g.encode(g.gen, compressed) * c
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# prepare_phase2: Groth16Params::new / ::write
+# ----------------------------------------------------------------------------------------------
+# ark-ff 0.4 MontConfig (ark-ff-macros montgomery/mod.rs): TWO_ADIC_ROOT_OF_UNITY = GENERATOR^t with
+# r - 1 = 2^s * t; GENERATOR = 22 for ark-bls12-377 Fr, 15 for ark-bls12-377 Fq (= ark-bw6-761 Fr) — the
+# smallest primitive roots (checked against the small prime factors of r - 1 in tests/test_oracle_cpu.py).
+FR_GENERATOR = {BLS12_377_R: 22, BLS12_377_Q: 15}
+
+
+def two_adicity(r: int) -> int:
+    s, t = 0, r - 1
+    while t % 2 == 0:
+        s, t = s + 1, t // 2
+    return s
+
+
+def get_root_of_unity(r: int, n: int) -> int:
+    """F::get_root_of_unity(n) (ark-ff fields/mod.rs, FftField): TWO_ADIC_ROOT_OF_UNITY squared down to order n."""
+    s = two_adicity(r)
+    log_n = n.bit_length() - 1
+    if n != 1 << log_n or log_n > s:
+        raise ValueError("no radix-2 domain of that size")
+    omega = pow(FR_GENERATOR[r], (r - 1) >> s, r)
+    for _ in range(log_n, s):
+        omega = omega * omega % r
+    return omega
+
+
+def domain_size(phase2_size: int) -> int:
+    """setup-utils/src/groth16_utils.rs:65-69: Radix2EvaluationDomain::new(n).size = n.next_power_of_two()."""
+    m = 1
+    while m < phase2_size:
+        m *= 2
+    return m
+
+
+def group_ifft(group: Group, pts):
+    """to_coeffs (setup-utils/src/groth16_utils.rs:44-53) by the definition of the inverse DFT:
+    out_j = (1/n) sum_i w^(-i*j) P_i.  O(n^2) scalar multiplications — small n only."""
+    n, r = len(pts), group.r
+    w_inv = pow(get_root_of_unity(r, n), -1, r)
+    n_inv = pow(n, -1, r)
+    out = []
+    for j in range(n):
+        acc = None
+        for i, P in enumerate(pts):
+            acc = group.add(acc, group.mul(P, pow(w_inv, i * j, r) * n_inv % r))
+        out.append(acc)
+    return out
+
+
+def group_ifft_fast(group: Group, pts):
+    """Same transform by recursive decimation in frequency (an algorithm independent of the device's
+    iterative decimation in time): n/2 log n scalar multiplications."""
+    n, r = len(pts), group.r
+    w_inv = pow(get_root_of_unity(r, n), -1, r)
+
+    def rec(v, w):
+        if len(v) == 1:
+            return v
+        h = len(v) // 2
+        even = [group.add(v[i], v[i + h]) for i in range(h)]
+        odd = [group.mul(group.add(v[i], group.neg(v[i + h])), pow(w, i, r)) for i in range(h)]
+        e, o = rec(even, w * w % r), rec(odd, w * w % r)
+        out = [None] * len(v)
+        out[0::2], out[1::2] = e, o
+        return out
+
+    n_inv = pow(n, -1, r)
+    return [group.mul(P, n_inv) for P in rec(list(pts), w_inv)]
+
+
+def scalar_ifft(r: int, vals):
+    """ark-poly domain.ifft on field elements (used to predict group_ifft of points with known discrete logs)."""
+    n = len(vals)
+    w_inv = pow(get_root_of_unity(r, n), -1, r)
+
+    def rec(v, w):
+        if len(v) == 1:
+            return v
+        h = len(v) // 2
+        ww = w * w % r
+        e = rec(v[0::2], ww)
+        o = rec(v[1::2], ww)
+        out = [0] * len(v)
+        t = 1
+        for i in range(h):
+            x = t * o[i] % r
+            out[i], out[i + h] = (e[i] + x) % r, (e[i] - x) % r
+            t = t * w % r
+        return out
+
+    n_inv = pow(n, -1, r)
+    return [x * n_inv % r for x in rec(list(vals), w_inv)]
+
+
+def h_query_groth16(group: Group, powers, degree: int):
+    """setup-utils/src/groth16_utils.rs:59-63: powers[i + degree] - powers[i] for i < degree - 1."""
+    return [group.add(powers[i + degree], group.neg(powers[i])) for i in range(degree - 1)]
+
+
+def groth16_params_new(params: "Phase1Parameters", acc: bytes, compressed_in, phase2_size: int, compressed_out,
+                       check=NO, ifft=None):
+    """Phase1::deserialize + Groth16Params::new + ::write (phase1/src/serialization.rs:23-41,
+    setup-utils/src/groth16_utils.rs:81-168; phase2-cli/src/prepare_phase2.rs:16-70)."""
+    cv = params.curve
+    ifft = ifft or group_ifft_fast
+    vecs = []
+    for vec, (o, c, s) in enumerate(params.split_offsets(compressed_in)):
+        g = cv.g2 if vec in (1, 4) else cv.g1
+        vecs.append(g.read_batch(acc[o:o + c * s], compressed_in, check))
+    tau_g1, tau_g2, alpha_g1, beta_g1, beta_g2 = vecs
+    m = domain_size(phase2_size)
+    if m > len(tau_g2):
+        raise InvalidLength("phase2 domain larger than the powers of tau")  # slice panic in the reference
+    out = bytearray()
+    out += cv.g1.write_batch([alpha_g1[0], beta_g1[0]], compressed_out)
+    out += cv.g2.write_batch([beta_g2[0]], compressed_out)
+    out += cv.g1.write_batch(ifft(cv.g1, tau_g1[:m]), compressed_out)
+    out += cv.g2.write_batch(ifft(cv.g2, tau_g2[:m]), compressed_out)
+    out += cv.g1.write_batch(ifft(cv.g1, alpha_g1[:m]), compressed_out)
+    out += cv.g1.write_batch(ifft(cv.g1, beta_g1[:m]), compressed_out)
+    out += cv.g1.write_batch(h_query_groth16(cv.g1, tau_g1, m), compressed_out)
+    return bytes(out)

@@ -37,6 +37,10 @@ from .ffi import (  # noqa: F401
     phase1_verification_vectors_dev,
     power_pairs,
     generate_powers_of_tau,
+    group_ifft,
+    groth16_params_new,
+    groth16_params_size,
+    h_query_groth16,
     lib,
     lib_path,
     phase1_aggregate_chunk,

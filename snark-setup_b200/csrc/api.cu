@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/snark_setup_b200.h"
+#include "fft.cuh"
 #include "msm.cuh"
 
 namespace {
@@ -1020,3 +1021,5 @@ int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, si
 }
 
 }  // extern "C"
+
+#include "api_fft.inl"

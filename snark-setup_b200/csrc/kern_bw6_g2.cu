@@ -1,4 +1,5 @@
 // Kernel instantiations for Bw6G2 (one translation unit per group keeps nvcc compile times parallel).
+#include "fft.cuh"
 #include "msm.cuh"
 
 namespace ss {
@@ -8,6 +9,10 @@ const GroupOps& ops_bw6_g2() {
 }
 const MsmOps& msm_ops_bw6_g2() {
     static const MsmOps o = MsmLaunch<Bw6G2>::ops();
+    return o;
+}
+const FftOps& fft_ops_bw6_g2() {
+    static const FftOps o = FftLaunch<Bw6G2>::ops();
     return o;
 }
 }  // namespace ss

@@ -249,6 +249,11 @@ struct ScalarMulArgs {
     const uint32_t* coeff_m;  // Montgomery coefficient (never null; 1 when absent)
     int has_coeff;
     uint32_t* jac;  // out: Jacobian, limb-major SoA [3*FW][n]
+    // group-FFT stages (fft.cuh): the exponent of thread i is first_power + (i & power_mask), and with
+    // src_log_m = s >= 0 thread i reads the upper element of butterfly i of a stage with half-size m = 2^s,
+    // aff[((i >> s) << (s + 1)) | m | (i & (m - 1))].  Defaults = plain batch_exp.
+    uint64_t power_mask = ~0ull;
+    int src_log_m = -1;
 };
 
 // bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
@@ -264,7 +269,12 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
     constexpr int FRW = FrP::N;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    Affine<F> base = load_affine<G>(a.aff, a.inf, a.n, i);
+    uint64_t src = i;
+    if (a.src_log_m >= 0) {
+        const uint64_t m = 1ull << a.src_log_m;
+        src = ((i >> a.src_log_m) << (a.src_log_m + 1)) | m | (i & (m - 1));
+    }
+    Affine<F> base = load_affine<G>(a.aff, a.inf, a.n, src);
     Fp<FrP> s;
     if (a.exps) {
 #pragma unroll
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
             s = fp_mul(s, c);  // canonical * Montgomery -> canonical
         }
     } else {
-        s = tau_power<FrP>(a.tau_tab, a.first_power + i);
+        s = tau_power<FrP>(a.tau_tab, a.first_power + (i & a.power_mask));
         if (a.has_coeff) {
             Fp<FrP> c;
 #pragma unroll
@@ -304,6 +314,10 @@ struct NormalizeArgs {
     uint32_t* out;     // serialized
     int out_compressed;
     uint32_t threads;  // T: thread t owns elements t, t+T, t+2T, ...
+    // when aff_out != nullptr the affine points go to an affine scratch (AoS + flag bytes, as k_decode
+    // writes it) instead of being serialized — intermediate stages of the group FFT (fft.cuh)
+    uint32_t* aff_out = nullptr;
+    uint8_t* inf_out = nullptr;
 };
 
 // CurveGroup::normalize_batch (Montgomery's trick, identities skipped) fused with
@@ -344,7 +358,12 @@ __global__ void __launch_bounds__(128) k_normalize_encode(NormalizeArgs a) {
             j.Y = FW::load(a.jac + (uint64_t)FW::W * n + e, n);
             p = jac_to_affine_with_zinv(j, zinv);
         }
-        encode_point<G>(a.out + e * owords, a.out_compressed != 0, p);
+        if (a.aff_out) {
+            store_affine<G>(a.aff_out, e, p);
+            a.inf_out[e] = p.inf ? 1 : 0;
+        } else {
+            encode_point<G>(a.out + e * owords, a.out_compressed != 0, p);
+        }
         if (e < T) break;
     }
 }

@@ -415,6 +415,54 @@ def phase1_decompress(params, inp, check=CHECK_NO):
     return bytes(out)
 
 
+def group_ifft(curve, group, inp, in_compressed, out_compressed, check=CHECK_NO):
+    """to_coeffs (setup-utils/src/groth16_utils.rs:44-53): group IFFT + normalize_batch -> bytes."""
+    f = lib().ss_group_ifft
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int]
+    n = len(inp) // element_size(curve, group, in_compressed)
+    out = bytearray(max(1, n) * element_size(curve, group, out_compressed))
+    pi, k1 = _buf(inp)
+    po, k2 = _buf(out)
+    _check(f(curve, group, pi, int(in_compressed), check, n, po, int(out_compressed)))
+    return bytes(out)
+
+
+def h_query_groth16(curve, powers, in_compressed, degree, out_compressed, check=CHECK_NO):
+    """h_query_groth16 (setup-utils/src/groth16_utils.rs:59-63) on serialized G1 powers -> bytes."""
+    f = lib().ss_h_query_groth16
+    f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
+    n = len(powers) // element_size(curve, G1, in_compressed)
+    out = bytearray(max(1, degree - 1) * element_size(curve, G1, out_compressed))
+    pi, k1 = _buf(powers)
+    po, k2 = _buf(out)
+    _check(f(curve, pi, int(in_compressed), check, n, degree, po, int(out_compressed)))
+    return bytes(out[:max(0, degree - 1) * element_size(curve, G1, out_compressed)])
+
+
+def groth16_params_size(curve, phase2_size, compressed):
+    """(domain_size, bytes written by Groth16Params::write) — setup-utils/src/groth16_utils.rs:65-69,134-168."""
+    f = lib().ss_groth16_params_size
+    f.argtypes = [C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]
+    m, b = C.c_uint64(0), C.c_size_t(0)
+    _check(f(curve, phase2_size, int(compressed), C.byref(m), C.byref(b)))
+    return m.value, b.value
+
+
+def groth16_params_new(params, accumulator, compressed_input, phase2_size, compressed_output, check=CHECK_NO):
+    """Groth16Params::new + ::write (setup-utils/src/groth16_utils.rs:81-168) = prepare_phase2
+    (phase2-cli/src/prepare_phase2.rs:16-70) -> the serialized parameters."""
+    f = lib().ss_groth16_params_new
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_size_t,
+                  C.c_int]
+    _, nbytes = groth16_params_size(params.curve, phase2_size, compressed_output)
+    out = bytearray(nbytes)
+    pi, k1 = _buf(accumulator)
+    po, k2 = _buf(out)
+    _check(f(C.byref(params.c), pi, len(accumulator), int(compressed_input), check, phase2_size, po, len(out),
+             int(compressed_output)))
+    return bytes(out)
+
+
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
                        tau, alpha, beta):
     """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place."""
