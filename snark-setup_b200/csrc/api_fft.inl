@@ -47,7 +47,7 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
     const size_t io_b = std::max(isz * nd, osz * n);  // staged input, later reused for the serialized output
     const size_t seq_b = (size_t)(log_n + 64) * frw * 4;
     const size_t need = 256 + align_up(io_b, 256) + align_up(2 * cw * nd, 256) + align_up(nd, 256) +
-                        align_up(2 * cw * n, 256) + align_up(n, 256) + align_up(3 * cw * std::max<uint64_t>(half, 1), 256) +
+                        align_up(2 * cw * n, 256) + align_up(n, 256) + align_up(3 * cw * std::max<uint64_t>(half, 2), 256) +
                         align_up(3 * cw * n, 256) + align_up(cw * n, 256) + align_up(seq_b, 256) + 256;
     size_t free_b = 0, total_b = 0;
     CU(cudaSetDevice(device));
@@ -63,7 +63,7 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
     uint8_t* inf_s = cv.take<uint8_t>(nd);
     uint32_t* aff = cv.take<uint32_t>(2 * cw * n);  // working set of the transform
     uint8_t* inf = cv.take<uint8_t>(n);
-    uint32_t* jac_t = cv.take<uint32_t>(3 * cw * std::max<uint64_t>(half, 1));
+    uint32_t* jac_t = cv.take<uint32_t>(3 * cw * std::max<uint64_t>(half, 2));
     uint32_t* jac_o = cv.take<uint32_t>(3 * cw * n);
     uint32_t* prefix = cv.take<uint32_t>(cw * n);
     uint32_t* seq = cv.take<uint32_t>(seq_b);
@@ -113,21 +113,24 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
         a.exps = nullptr;
         a.first_power = 0;
         a.coeff_m = ninv_m;
-        // every point times n^-1 (ifft's final scaling, applied first: w_s^0 = 1 makes stage 0 free of twiddles)
-        a.n = n;
+        // ifft's scaling by n^-1 rides on the twiddles: block 0 of stage s is lo + t with lo = block 0 of
+        // stage s-1 (already scaled, by induction) and t = (n^-1 * w_s^j) * hi, one Fr multiplication more per
+        // thread; only elements 0 and 1 (stage 0 has no twiddles) are scaled by a scalar multiplication of their own.
+        a.n = 2;
         a.tau_tab = seq;
         a.has_coeff = 1;
         a.power_mask = 0;
         a.src_log_m = -1;
-        a.jac = jac_o;
-        { ProfScope ps("k_scalar_mul", o.name, n, s); o.scalar_mul(a, s); }
-        normalize(jac_o, n, nullptr);
+        a.jac = jac_t;
+        { ProfScope ps("k_scalar_mul", o.name, 2, s); o.scalar_mul(a, s); }
+        normalize(jac_t, 2, nullptr);
         for (int st_i = 0; st_i < log_n; st_i++) {
             const uint32_t* tw = nullptr;
             if (st_i > 0) {
                 a.n = half;
                 a.tau_tab = seq + (size_t)(log_n - 1 - st_i) * frw;  // table of w_s^(2^j), w_s = w^(-n/2m)
-                a.has_coeff = 0;
+                a.has_coeff = 1;
+                a.coeff_limit = 1ull << st_i;  // block 0
                 a.power_mask = (1ull << st_i) - 1;
                 a.src_log_m = st_i;
                 a.jac = jac_t;

@@ -8,14 +8,16 @@
 // see FrP::fft_root), and the outputs cross the boundary as canonical affine bytes, so any exact algorithm
 // is bit-identical to arkworks' in_order_ifft_in_place.  Here: radix-2 decimation in time.
 //   1. bit-reversal gather of the decoded points                                  k_fft_bitrev   (HBM-bound)
-//   2. every point times n^-1 (one k_scalar_mul pass, GLV/GLS), normalised to affine again
-//   3. stage s = 0 .. log n - 1 (half-size m = 2^s, w_s = w^(-n/2m)):
+//   2. stage s = 0 .. log n - 1 (half-size m = 2^s, w_s = w^(-n/2m)):
 //        t_i  = w_s^(i mod m) * upper_i      k_scalar_mul on n/2 gathered elements (skipped for s = 0: w_0^0 = 1)
 //        lo', hi' = lo + t, lo - t           k_fft_butterfly, two mixed additions (exceptional cases handled)
 //        batch-normalise to affine           k_normalize_encode -> affine scratch (last stage: serialized bytes)
+//   The final scaling by n^-1 costs no scalar multiplications of its own: block 0 of every stage uses the
+//   twiddles n^-1 * w_s^j (its lower half is block 0 of the previous stage, already scaled), and only
+//   elements 0 and 1 are multiplied by n^-1 directly before the twiddle-free stage 0.
 // Twiddle scalars are never materialised: thread i derives w_s^(i mod m) from the table of w_s^(2^j), which for
 // every stage is a window of ONE sequence seq[j] = (w^-1)^(2^j) (w_s^(2^j) = seq[log n - 1 - s + j]).
-// Work: n + (log n - 1) * n/2 scalar multiplications — the integer-multiply pipe bounds it like batch_exp.
+// Work: (log n - 1) * n/2 + 2 scalar multiplications — the integer-multiply pipe bounds it like batch_exp.
 #pragma once
 #include "kernels.cuh"
 

@@ -252,8 +252,10 @@ struct ScalarMulArgs {
     // group-FFT stages (fft.cuh): the exponent of thread i is first_power + (i & power_mask), and with
     // src_log_m = s >= 0 thread i reads the upper element of butterfly i of a stage with half-size m = 2^s,
     // aff[((i >> s) << (s + 1)) | m | (i & (m - 1))].  Defaults = plain batch_exp.
+    // The coefficient is applied to threads i < coeff_limit only (the 1/n of an IFFT rides on block 0's twiddles).
     uint64_t power_mask = ~0ull;
     int src_log_m = -1;
+    uint64_t coeff_limit = ~0ull;
 };
 
 // bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
         }
     } else {
         s = tau_power<FrP>(a.tau_tab, a.first_power + (i & a.power_mask));
-        if (a.has_coeff) {
+        if (a.has_coeff && i < a.coeff_limit) {
             Fp<FrP> c;
 #pragma unroll
             for (int k = 0; k < FRW; k++) c.l[k] = __ldg(a.coeff_m + k);

@@ -84,6 +84,66 @@ def phase2(log2n):
                       "ratio_check": rok, "path": "host buffers through ss_batch_mul / ss_merge_pairs"}), flush=True)
 
 
+def prepare_phase2(curve, power):
+    """Groth16Params::new + ::write (prepare_phase2) of a 2^power accumulator with phase2_size = 2^power."""
+    from snark_setup_b200 import ffi as F
+    cv = R.CURVES[curve]
+    cid = S.BLS12_377 if curve == "bls12_377" else S.BW6_761
+    rp = R.Phase1Parameters(cv, power, 256)
+    sp = S.Phase1Parameters(cid, power, 256)
+    m = 1 << power
+    keys = [scalar(b"pp2-%d" % i, cv.r) for i in range(3)]
+    acc = bytearray(sp.get_length(False))
+    S.phase1_computation(sp, bytes(R.phase1_initialization(rp, False)), acc, False, False, S.CHECK_NO, *keys)
+    acc = bytes(acc)
+    out = []
+    S.groth16_params_new(sp, acc, False, m, False)  # warm-up (slab allocation)
+    t0 = time.perf_counter()
+    out.append(S.groth16_params_new(sp, acc, False, m, False))
+    t = time.perf_counter() - t0
+    F.profile_enable(True)
+    F.profile_reset()
+    S.groth16_params_new(sp, acc, False, m, False)
+    prof = {k: round(v["ms"], 3) for k, v in sorted(F.profile_read().items())}
+    F.profile_enable(False)
+    # forward-evaluation check of the tau_g1 coefficients at w^1: sum_j w^j coeffs_j = tau*G
+    s1, s2 = cv.g1.size(False), cv.g2.size(False)
+    w = R.get_root_of_unity(cv.r, m)
+    rho, x = [], 1
+    for _ in range(m):
+        rho.append(x)
+        x = x * w % cv.r
+    coeffs = out[0][2 * s1 + s2:2 * s1 + s2 + m * s1]
+    s_, _ = S.merge_pairs(cid, S.G1, coeffs, coeffs, False, rho=rho)
+    o = rp.split_offsets(False)[0][0]
+    ok = s_ == acc[o + s1:o + 2 * s1]
+    smuls = 4 * ((power - 1) * m // 2 + 2)
+    # CPU port: the reference algorithm spends n/2*log n full scalar multiplications per vector (ark-poly's
+    # radix-2 FFT over C::Group) + n for the 1/n scaling; time a sample of them on the host cores
+    k = 1 << 12
+    gens = cv.g1.encode(cv.g1.gen, False) * k
+    t1 = time.perf_counter()
+    O.apply_powers(cid, 0, gens, False, 3, False, k, tau=keys[0], first_power=1)
+    t_g1 = (time.perf_counter() - t1) / k
+    gens2 = cv.g2.encode(cv.g2.gen, False) * k
+    t1 = time.perf_counter()
+    O.apply_powers(cid, 1, gens2, False, 3, False, k, tau=keys[0], first_power=1)
+    t_g2 = (time.perf_counter() - t1) / k
+    per_vec = m * power // 2 + m
+    cpu_s = per_vec * (3 * t_g1 + t_g2)
+    print(json.dumps({"bench": "prepare_phase2 (Groth16Params::new + write)", "curve": curve, "power": power,
+                      "phase2_size": m, "seconds": round(t, 4), "coefficients_per_s": round(4 * m / t),
+                      "scalar_muls": smuls, "output_bytes": len(out[0]), "forward_evaluation_check": ok,
+                      "kernels_ms": prof,
+                      "cpu_port_estimate_s": round(cpu_s, 1), "cpu_cores": O.threads(),
+                      "cpu_note": "C++ oracle scalar-mul rate on the host cores x the reference algorithm's "
+                                  "n/2*log n + n multiplications per vector (3 G1 + 1 G2)",
+                      "path": "host buffers through ss_groth16_params_new"}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "prepare_phase2":
+        prepare_phase2(sys.argv[2] if len(sys.argv) > 2 else "bls12_377", int(sys.argv[3]) if len(sys.argv) > 3 else 18)
+        sys.exit(0)
     bw6(int(sys.argv[1]) if len(sys.argv) > 1 else 16)
     phase2(int(sys.argv[2]) if len(sys.argv) > 2 else 20)
