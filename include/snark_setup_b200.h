@@ -56,7 +56,8 @@ typedef enum {
     SS_ERR_INVALID_CHUNK = 6,      /* Error::InvalidChunk                             */
     SS_ERR_BATCH_TOO_SMALL = 7,    /* Error::BatchTooSmall                            */
     SS_ERR_INVALID_ARGUMENT = 8,   /* (no reference equivalent: bad enum / null pointer)  */
-    SS_ERR_DEVICE = 9              /* CUDA failure; the Rust shim turns this into a panic */
+    SS_ERR_DEVICE = 9,             /* CUDA failure; the Rust shim turns this into a panic */
+    SS_ERR_INVALID_RATIO = 10      /* VerificationError::InvalidRatio (setup-utils/src/errors.rs:97-100) */
 } ss_status;
 
 typedef struct {
@@ -262,6 +263,24 @@ int ss_groth16_params_size(int curve, uint64_t phase2_size, int compressed, uint
 int ss_groth16_params_new(const ss_phase1_params* p, const uint8_t* accumulator, size_t accumulator_len,
                           int compressed_input, int check, uint64_t phase2_size, uint8_t* out, size_t out_len,
                           int compressed_output);
+
+/* -------------------------------------------------------------------------------------------- */
+/* ratio checks by pairing                                       */
+/* -------------------------------------------------------------------------------------------- */
+/* same_ratio — setup-utils/src/helpers.rs:406-408: *same = (e(g1.0, g2.1) == e(g1.1, g2.0)).
+ * g1_pair = g1.0 || g1.1 and g2_pair = g2.0 || g2.1, UNCOMPRESSED elements (what ss_power_pairs /
+ * ss_merge_pairs / ss_phase1_verification_vectors return).  The device evaluates a reduced Tate pairing
+ * product; the verdict is the same for every non-degenerate pairing on G1 x G2.  Inputs must be subgroup
+ * points (the callers have checked that), e(O, .) = 1. */
+int ss_same_ratio(int curve, const uint8_t* g1_pair, const uint8_t* g2_pair, int* same);
+
+/* check_same_ratio — setup-utils/src/helpers.rs:410-424: SS_ERR_INVALID_RATIO when one of the four points
+ * is zero or the pairings differ. */
+int ss_check_same_ratio(int curve, const uint8_t* g1_pair, const uint8_t* g2_pair);
+
+/* `count` independent checks in one launch (one warp each), e.g. the four vectors of a response;
+ * *first_bad = index of the first failing check. */
+int ss_check_same_ratio_batch(int curve, const uint8_t* g1_pairs, const uint8_t* g2_pairs, int count, int* first_bad);
 
 #ifdef __cplusplus
 }

@@ -818,3 +818,119 @@ def groth16_params_new(params: "Phase1Parameters", acc: bytes, compressed_in, ph
     out += cv.g1.write_batch(ifft(cv.g1, beta_g1[:m]), compressed_out)
     out += cv.g1.write_batch(h_query_groth16(cv.g1, tau_g1, m), compressed_out)
     return bytes(out)
+
+
+# ----------------------------------------------------------------------------------------------
+# same_ratio / check_same_ratio (setup-utils/src/helpers.rs:406-424) — SURVEY.md §8 A12, §8f rank 2
+# ----------------------------------------------------------------------------------------------
+# The reference compares E::pairing(g1.0, g2.1) with E::pairing(g1.1, g2.0) (arkworks' optimal ate pairings).
+# Only the VERDICT crosses the boundary, and every non-degenerate bilinear pairing on G1 x G2 gives the same
+# verdict, so the oracle uses the textbook reduced Tate pairing: affine Miller loop over r on E(Fq), lines
+# evaluated at the untwisted G2 point in Fq^k = F[w]/(w^6 - xi), and the plain exponentiation by (q^k - 1)/r.
+class ExtW6:
+    """F[w]/(w^6 - xi) over F = Fp (BW6-761, k = 6) or Fp2 (BLS12-377, k = 12); elements are 6-lists."""
+
+    def __init__(self, F, xi):
+        self.F, self.xi = F, xi
+
+    def one(self):
+        F = self.F
+        return [F.one] + [F.zero] * 5
+
+    def mul(self, a, b):
+        F = self.F
+        acc = [F.zero] * 11
+        for i, ai in enumerate(a):
+            if F.is_zero(ai):
+                continue
+            for j, bj in enumerate(b):
+                if not F.is_zero(bj):
+                    acc[i + j] = F.add(acc[i + j], F.mul(ai, bj))
+        return [F.add(acc[k], F.mul(self.xi, acc[k + 6])) if k < 5 else acc[k] for k in range(6)]
+
+    def pow(self, a, e):
+        r = self.one()
+        for bit in bin(e)[2:]:
+            r = self.mul(r, r)
+            if bit == "1":
+                r = self.mul(r, a)
+        return r
+
+
+def pairing_tower(curve: Curve):
+    """(ExtW6, embedding degree, twist type) — ark-bls12-377: Fq12 = Fq2[v]/(v^3-u)[w]/(w^2-v), D-type twist;
+    ark-bw6-761: Fq6 = Fq[v]/(v^3+4)[w]/(w^2-v), M-type twist."""
+    F = curve.g2.F
+    if curve.name == "bls12_377":
+        return ExtW6(F, (0, 1)), 12, "D"
+    return ExtW6(F, F.from_int(-4)), 6, "M"
+
+
+def untwist(curve: Curve, Q):
+    """G2 point on the twist -> (x, y) on E(Fq^k) as ExtW6 elements."""
+    K, _, tw = pairing_tower(curve)
+    F = K.F
+    x, y = [F.zero] * 6, [F.zero] * 6
+    if tw == "D":      # (x', y') -> (x' w^2, y' w^3)
+        x[2], y[3] = Q[0], Q[1]
+    else:              # (x', y') -> (x' / w^2, y' / w^3) = (x' w^4 / xi, y' w^3 / xi)
+        xi_inv = F.inv(K.xi)
+        x[4], y[3] = F.mul(Q[0], xi_inv), F.mul(Q[1], xi_inv)
+    return x, y
+
+
+def tate_miller(curve: Curve, P, Q):
+    """f_{r,P}(Q) without vertical lines (denominator elimination); P in G1, Q in G2; identity -> 1."""
+    K, _, _ = pairing_tower(curve)
+    F, g1 = K.F, curve.g1
+    if P is None or Q is None:
+        return K.one()
+    xq, yq = untwist(curve, Q)
+    emb = (lambda v: (v, 0)) if F.degree == 2 else (lambda v: v)
+    Fq = g1.F
+
+    def line(T, lam):
+        # y_Q - y_T - lam (x_Q - x_T)
+        c = [F.sub(yq[k], F.mul(emb(lam), xq[k])) for k in range(6)]
+        c[0] = F.add(c[0], emb(Fq.sub(Fq.mul(lam, T[0]), T[1])))
+        return c
+
+    f, T = K.one(), P
+    bits = bin(curve.r)[3:]
+    for n, bit in enumerate(bits):
+        lam = Fq.mul(Fq.mul(3, Fq.sqr(T[0])), Fq.inv(Fq.mul(2, T[1])))
+        f = K.mul(K.mul(f, f), line(T, lam))
+        T = g1.add(T, T)
+        if bit == "1" and n != len(bits) - 1:  # the last addition, T = -P, is a vertical line
+            lam = Fq.mul(Fq.sub(T[1], P[1]), Fq.inv(Fq.sub(T[0], P[0])))
+            f = K.mul(f, line(T, lam))
+            T = g1.add(T, P)
+    assert T == g1.neg(P)
+    return f
+
+
+def pairing(curve: Curve, P, Q):
+    """Reduced Tate pairing t(P, Q) = f_{r,P}(Q)^((q^k - 1)/r)."""
+    K, k, _ = pairing_tower(curve)
+    q = curve.g1.F.p
+    return K.pow(tate_miller(curve, P, Q), (q ** k - 1) // curve.r)
+
+
+def same_ratio(curve: Curve, g1_pair, g2_pair) -> bool:
+    """setup-utils/src/helpers.rs:406-408: e(g1.0, g2.1) == e(g1.1, g2.0), as e(g1.0, g2.1) * e(-g1.1, g2.0) == 1."""
+    K, k, _ = pairing_tower(curve)
+    q = curve.g1.F.p
+    f = K.mul(tate_miller(curve, g1_pair[0], g2_pair[1]), tate_miller(curve, curve.g1.neg(g1_pair[1]), g2_pair[0]))
+    return K.pow(f, (q ** k - 1) // curve.r) == K.one()
+
+
+class InvalidRatio(SetupError):          # VerificationError::InvalidRatio
+    pass
+
+
+def check_same_ratio(curve: Curve, g1_pair, g2_pair):
+    """setup-utils/src/helpers.rs:410-424."""
+    if any(P is None for P in (*g1_pair, *g2_pair)):
+        raise InvalidRatio("zero")
+    if not same_ratio(curve, g1_pair, g2_pair):
+        raise InvalidRatio("wrong pairing")

@@ -21,6 +21,7 @@ from .ffi import (  # noqa: F401
     IncorrectSubgroup,
     InvalidData,
     InvalidLength,
+    InvalidRatio,
     Phase1Parameters,
     PointAtInfinity,
     SetupError,
@@ -30,6 +31,9 @@ from .ffi import (  # noqa: F401
     batch_mul,
     build,
     check_and_ratio,
+    check_same_ratio,
+    check_same_ratio_batch,
+    same_ratio,
     check_subgroup,
     element_size,
     merge_pairs,

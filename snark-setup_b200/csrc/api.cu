@@ -28,6 +28,7 @@
 #include "../../include/snark_setup_b200.h"
 #include "fft.cuh"
 #include "msm.cuh"
+#include "pairing.cuh"
 
 namespace {
 
@@ -1023,3 +1024,4 @@ int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, si
 }  // extern "C"
 
 #include "api_fft.inl"
+#include "api_pairing.inl"

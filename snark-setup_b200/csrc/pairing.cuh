@@ -1,0 +1,216 @@
+// same_ratio / check_same_ratio on the device (setup-utils/src/helpers.rs:406-424).
+//
+// The reference compares two optimal-ate pairings, E::pairing(g1.0, g2.1) == E::pairing(g1.1, g2.0).  Only the
+// verdict crosses the boundary and every non-degenerate bilinear pairing on G1 x G2 gives the same one, so this
+// kernel evaluates the reduced TATE pairing product
+//        ( f_{r,g1.0}(psi(g2.1)) * f_{r,-g1.1}(psi(g2.0)) ) ^ ((q^k - 1)/r)  ==  1
+// which needs nothing but the G1 group law already in ec.cuh and one extension-field multiplication:
+//   * Fq^k = F[w]/(w^6 - xi) with F = Fq2, xi = u (BLS12-377: ark's Fq12 = Fq2[v]/(v^3-u)[w]/(w^2-v)) or F = Fq,
+//     xi = -4 (BW6-761: Fq6 = Fq[v]/(v^3+4)[w]/(w^2-v)); psi = untwist, (x', y') -> (x' w^2, y' w^3) for the D-type
+//     twist of BLS12-377 and (x' w^4/xi, y' w^3/xi) for the M-type twist of BW6-761.
+//   * One WARP per ratio check, lane k (mod 6) owns coefficient k of the running value: a product is 6
+//     F-multiplications per lane with the operands exchanged by warp shuffles, the sparse line multiplication 3.
+//     The G1 Miller points (Jacobian, shared doubling/addition formulas) are computed redundantly by every lane.
+//   * Lines are scaled by Fq factors (killed by the final exponentiation, as are the vertical lines):
+//       tangent at T = (X, Y, Z):      (3X^3 - 2Y^2)  -  3X^2 Z^2 * x_Q  +  2YZ^3 * y_Q
+//       chord through T and P:         (N x_P - D y_P) -  N * x_Q        +  D * y_Q,   N = Y - y_P Z^3, D = Z (X - x_P Z^2)
+//   * Final exponentiation: f^(q^(k/2)-1) = conj(f)/f (norm to the cubic subfield, one F inversion), then
+//     f^(Q+1) with Q = q^2 (k = 12) / q (k = 6) through the Frobenius multipliers zeta^k (in Fq), then the
+//     hard part Phi_k(q)/r by square-and-multiply (1255 / 1144 bits; exponent from tools/gen_constants.py).
+// O(1) work per verification (4 checks per response): latency, not throughput, is what matters here.
+#pragma once
+#include "codec.cuh"
+
+namespace ss {
+
+template <class P>
+SS_D Fp<P> lane_get(const Fp<P>& a, int src) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.l[i] = __shfl_sync(0xffffffffu, a.l[i], src);
+    return r;
+}
+template <class P>
+SS_D Fp2<P> lane_get(const Fp2<P>& a, int src) {
+    return Fp2<P>{lane_get(a.c0, src), lane_get(a.c1, src)};
+}
+template <class P>
+SS_D Fp<P> fscale(const Fp<P>& a, const Fp<P>& s) {
+    return fp_mul(a, s);
+}
+template <class P>
+SS_D Fp2<P> fscale(const Fp2<P>& a, const Fp<P>& s) {
+    return Fp2<P>{fp_mul(a.c0, s), fp_mul(a.c1, s)};
+}
+
+struct Bls377Pairing {
+    using G1 = Bls377G1;
+    using G2 = Bls377G2;
+    using Fq = Fp<Bls377Fq>;
+    using F = Fp2<Bls377Fq>;
+    using PP = Bls377PairingParams;
+    static constexpr int XPOS = 2;               // D-type: x_Q = x' w^2, y_Q = y' w^3
+    static constexpr bool XI_ON_CONST = false;
+    SS_D static F mul_xi(const F& a) { return F{fp_neg(fp_mul5(a.c1)), a.c0}; }  // xi = u, u^2 = -5
+};
+struct Bw6Pairing {
+    using G1 = Bw6G1;
+    using G2 = Bw6G2;
+    using Fq = Fp<Bw6Fq>;
+    using F = Fp<Bw6Fq>;
+    using PP = Bw6PairingParams;
+    static constexpr int XPOS = 4;               // M-type: xi x_Q = x' w^4, xi y_Q = y' w^3 (whole line scaled by xi)
+    static constexpr bool XI_ON_CONST = true;
+    SS_D static F mul_xi(const F& a) { return fp_neg(fp_dbl(fp_dbl(a))); }  // xi = -4
+};
+
+// c = a * b in F[w]/(w^6 - xi); every lane passes its own coefficient (lane k mod 6 <-> w^k)
+template <class C>
+SS_D typename C::F ext_mul(const typename C::F& a, const typename C::F& b, int k) {
+    using F = typename C::F;
+    F lo = F::zero(), hi = F::zero();  // hi collects the terms with i + j >= 6 (one multiplication by xi at the end)
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+        int j = k - i;
+        const bool wrap = j < 0;
+        if (wrap) j += 6;
+        F t = fp_mul(lane_get(a, i), lane_get(b, j));
+        if (wrap) hi = fp_add(hi, t);
+        else lo = fp_add(lo, t);
+    }
+    return fp_add(lo, C::mul_xi(hi));
+}
+
+// f * (s0 + lx w^XPOS + ly w^3), s0 in Fq (times xi for the M-type twist), lx, ly in F
+template <class C>
+SS_D typename C::F ext_mul_line(const typename C::F& f, const typename C::Fq& s0, const typename C::F& lx,
+                                const typename C::F& ly, int k) {
+    using F = typename C::F;
+    F c = fscale(f, s0);
+    if (C::XI_ON_CONST) c = C::mul_xi(c);
+    {
+        int j = k - 3;
+        const bool wrap = j < 0;
+        if (wrap) j += 6;
+        F t = fp_mul(lane_get(f, j), ly);
+        c = fp_add(c, wrap ? C::mul_xi(t) : t);
+    }
+    {
+        int j = k - C::XPOS;
+        const bool wrap = j < 0;
+        if (wrap) j += 6;
+        F t = fp_mul(lane_get(f, j), lx);
+        c = fp_add(c, wrap ? C::mul_xi(t) : t);
+    }
+    return c;
+}
+
+// verdict bits: 1 = same ratio, 2 = one of the four points is the identity (check_same_ratio rejects those)
+template <class C>
+__global__ void __launch_bounds__(32) k_same_ratio(const uint32_t* g1_pairs, const uint32_t* g2_pairs, int count,
+                                                   int* verdict) {
+    using F = typename C::F;
+    using Fq = typename C::Fq;
+    using G1 = typename C::G1;
+    using G2 = typename C::G2;
+    using PP = typename C::PP;
+    const int b = blockIdx.x;
+    if (b >= count) return;
+    const int lane = threadIdx.x, k = lane % 6;
+    Affine<Fq> P[2];
+    Affine<F> Q[2];
+    {
+        Affine<Fq> a0, a1;
+        Affine<F> b0, b1;
+        const uint32_t* p1 = g1_pairs + (size_t)b * 2 * (G1::USIZE / 4);
+        const uint32_t* p2 = g2_pairs + (size_t)b * 2 * (G2::USIZE / 4);
+        int e = decode_point<G1>(p1, false, CHECK_NO, a0) | decode_point<G1>(p1 + G1::USIZE / 4, false, CHECK_NO, a1) |
+                decode_point<G2>(p2, false, CHECK_NO, b0) | decode_point<G2>(p2 + G2::USIZE / 4, false, CHECK_NO, b1);
+        if (e != ERR_OK) {  // non-canonical field bytes
+            if (lane == 0) verdict[b] = -e;
+            return;
+        }
+        const bool lhs_one = a0.inf || b1.inf, rhs_one = a1.inf || b0.inf;
+        if (lhs_one || rhs_one) {  // e(O, .) = 1 and e(P, Q) != 1 for non-zero subgroup points
+            if (lane == 0) verdict[b] = 2 | ((lhs_one && rhs_one) ? 1 : 0);
+            return;
+        }
+        P[0] = a0;
+        Q[0] = b1;
+        P[1] = affine_neg(a1);
+        Q[1] = b0;
+    }
+    Jac<Fq> T[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) T[j] = Jac<Fq>{P[j].x, P[j].y, Fq::one()};
+    F f = k == 0 ? F::one() : F::zero();
+#pragma unroll 1
+    for (int i = G1::GP::ORDER_BITS - 2; i >= 0; i--) {
+        f = ext_mul<C>(f, f, k);
+#pragma unroll 1
+        for (int j = 0; j < 2; j++) {
+            const Jac<Fq>& t = T[j];
+            Fq X2 = fp_sqr(t.X), Y2 = fp_sqr(t.Y), Z2 = fp_sqr(t.Z);
+            Fq X2_3 = fp_add(fp_dbl(X2), X2);
+            Fq s0 = fp_sub(fp_mul(X2_3, t.X), fp_dbl(Y2));
+            Fq sx = fp_neg(fp_mul(X2_3, Z2));
+            Fq sy = fp_dbl(fp_mul(fp_mul(t.Y, t.Z), Z2));
+            f = ext_mul_line<C>(f, s0, fscale(Q[j].x, sx), fscale(Q[j].y, sy), k);
+            T[j] = jac_dbl(t);
+        }
+        const bool bit = (G1::GP::order(i >> 5) >> (i & 31)) & 1;
+        if (bit && i != 0) {  // the last addition (T = -P) is a vertical line
+#pragma unroll 1
+            for (int j = 0; j < 2; j++) {
+                const Jac<Fq>& t = T[j];
+                Fq Z2 = fp_sqr(t.Z);
+                Fq N = fp_sub(t.Y, fp_mul(P[j].y, fp_mul(Z2, t.Z)));
+                Fq D = fp_mul(t.Z, fp_sub(t.X, fp_mul(P[j].x, Z2)));
+                Fq s0 = fp_sub(fp_mul(N, P[j].x), fp_mul(D, P[j].y));
+                f = ext_mul_line<C>(f, s0, fscale(Q[j].x, fp_neg(N)), fscale(Q[j].y, D), k);
+                T[j] = jac_madd(t, P[j]);
+            }
+        }
+    }
+    // ---- final exponentiation ----
+    F fc = (k & 1) ? fp_neg(f) : f;  // f^(q^(k/2)): w -> -w
+    F nrm = ext_mul<C>(f, fc, k);    // in the cubic subfield F[v]/(v^3 - xi), v = w^2: coefficients 0, 2, 4
+    F n0 = lane_get(nrm, 0), n1 = lane_get(nrm, 2), n2 = lane_get(nrm, 4);
+    F t0 = fp_sub(fp_sqr(n0), C::mul_xi(fp_mul(n1, n2)));
+    F t1 = fp_sub(C::mul_xi(fp_sqr(n2)), fp_mul(n0, n1));
+    F t2 = fp_sub(fp_sqr(n1), fp_mul(n0, n2));
+    F d = fp_add(fp_mul(n0, t0), C::mul_xi(fp_add(fp_mul(n2, t1), fp_mul(n1, t2))));
+    F di = fp_inv(d);
+    F ninv = k == 0 ? fp_mul(t0, di) : k == 2 ? fp_mul(t1, di) : k == 4 ? fp_mul(t2, di) : F::zero();
+    F finv = ext_mul<C>(fc, ninv, k);
+    F f1 = ext_mul<C>(fc, finv, k);  // f^(q^(k/2) - 1)
+    Fq z;
+#pragma unroll
+    for (int i = 0; i < Fq::N; i++) z.l[i] = PP::frob(k, i);
+    F f2 = ext_mul<C>(fscale(f1, z), f1, k);  // f1^(Q + 1): (sum c_k w^k)^Q = sum c_k zeta^k w^k
+    F acc = f2;
+#pragma unroll 1
+    for (int i = PP::HARD_BITS - 2; i >= 0; i--) {
+        acc = ext_mul<C>(acc, acc, k);
+        if ((PP::hard(i >> 5) >> (i & 31)) & 1) acc = ext_mul<C>(acc, f2, k);
+    }
+    const bool ok = k == 0 ? (acc == F::one()) : acc.is_zero();
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) verdict[b] = all_ok ? 1 : 0;
+}
+
+struct PairingOps {
+    void (*same_ratio)(const uint32_t* g1_pairs, const uint32_t* g2_pairs, int count, int* verdict, cudaStream_t);
+};
+template <class C>
+struct PairingLaunch {
+    static void same_ratio(const uint32_t* g1_pairs, const uint32_t* g2_pairs, int count, int* verdict, cudaStream_t s) {
+        if (count > 0) k_same_ratio<C><<<count, 32, 0, s>>>(g1_pairs, g2_pairs, count, verdict);
+    }
+    static PairingOps ops() { return PairingOps{&same_ratio}; }
+};
+
+const PairingOps& pairing_ops_bls377();
+const PairingOps& pairing_ops_bw6();
+
+}  // namespace ss

@@ -38,10 +38,11 @@ class InvalidChunk(SetupError): pass         # noqa: E701
 class BatchTooSmall(SetupError): pass        # noqa: E701
 class InvalidArgument(SetupError): pass      # noqa: E701
 class DeviceError(SetupError): pass          # noqa: E701
+class InvalidRatio(SetupError): pass         # noqa: E701  (VerificationError::InvalidRatio)
 
 
 _ERRORS = {1: InvalidData, 2: UnexpectedFlags, 3: PointAtInfinity, 4: IncorrectSubgroup, 5: InvalidLength,
-           6: InvalidChunk, 7: BatchTooSmall, 8: InvalidArgument, 9: DeviceError}
+           6: InvalidChunk, 7: BatchTooSmall, 8: InvalidArgument, 9: DeviceError, 10: InvalidRatio}
 
 
 class _ErrInfo(C.Structure):
@@ -461,6 +462,31 @@ def groth16_params_new(params, accumulator, compressed_input, phase2_size, compr
     _check(f(C.byref(params.c), pi, len(accumulator), int(compressed_input), check, phase2_size, po, len(out),
              int(compressed_output)))
     return bytes(out)
+
+
+def same_ratio(curve, g1_pair, g2_pair):
+    """setup-utils/src/helpers.rs:406-408; g1_pair / g2_pair = two uncompressed elements each -> bool."""
+    f = lib().ss_same_ratio
+    f.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    same = C.c_int(0)
+    _check(f(curve, bytes(g1_pair), bytes(g2_pair), C.byref(same)))
+    return bool(same.value)
+
+
+def check_same_ratio(curve, g1_pair, g2_pair):
+    """setup-utils/src/helpers.rs:410-424; raises InvalidRatio."""
+    f = lib().ss_check_same_ratio
+    f.argtypes = [C.c_int, C.c_char_p, C.c_char_p]
+    _check(f(curve, bytes(g1_pair), bytes(g2_pair)))
+
+
+def check_same_ratio_batch(curve, g1_pairs, g2_pairs):
+    """Several check_same_ratio in one launch; raises InvalidRatio with .index = first failing check."""
+    f = lib().ss_check_same_ratio_batch
+    f.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+    n = len(g1_pairs) // (2 * element_size(curve, G1, False))
+    bad = C.c_int(-1)
+    _check(f(curve, bytes(g1_pairs), bytes(g2_pairs), n, C.byref(bad)))
 
 
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
