@@ -282,6 +282,17 @@ int ss_check_same_ratio(int curve, const uint8_t* g1_pair, const uint8_t* g2_pai
  * *first_bad = index of the first failing check. */
 int ss_check_same_ratio_batch(int curve, const uint8_t* g1_pairs, const uint8_t* g2_pairs, int count, int* first_bad);
 
+/* The per-vector half of Phase1::verification WITH its verdict (phase1/src/verification.rs:44-80,217-411):
+ * ss_phase1_verification_vectors followed by check_power_ratios / check_power_ratios_g2 for every vector
+ * (phase1/src/helpers/accumulator.rs:56-91) against g2_check = (tau_g2[0], tau_g2[1]) and
+ * g1_check = (tau_g1[0], tau_g1[1]) read from the response with `check_output` (verification.rs:58-71).
+ * SS_ERR_INVALID_RATIO: ss_last_error().index = 0 tau_g1, 1 tau_g2, 2 alpha_g1, 3 beta_g1.  The proof-of-knowledge
+ * and before/after checks on the first elements (verification.rs:83-213) need hash_to_g2 and stay with the
+ * caller, who can run their check_same_ratio through ss_check_same_ratio_batch. */
+int ss_phase1_verification_ratios(const ss_phase1_params* p, const uint8_t* output, size_t output_len, int compressed_output,
+                                  int check_output, uint8_t* new_challenge, size_t new_challenge_len,
+                                  int compressed_new_challenge, int subgroup_mode, const uint8_t* rho_seed);
+
 #ifdef __cplusplus
 }
 #endif

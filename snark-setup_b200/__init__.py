@@ -37,6 +37,7 @@ from .ffi import (  # noqa: F401
     check_subgroup,
     element_size,
     merge_pairs,
+    phase1_verification_ratios,
     phase1_verification_vectors,
     phase1_verification_vectors_dev,
     power_pairs,

@@ -489,6 +489,20 @@ def check_same_ratio_batch(curve, g1_pairs, g2_pairs):
     _check(f(curve, bytes(g1_pairs), bytes(g2_pairs), n, C.byref(bad)))
 
 
+def phase1_verification_ratios(params, output, compressed_output, new_challenge, compressed_new_challenge,
+                               check_output=CHECK_FULL, subgroup_mode=SUBGROUP_AUTO, seed=None):
+    """Per-vector half of Phase1::verification with its verdict (phase1/src/verification.rs:44-80,217-411):
+    raises PointAtInfinity / IncorrectSubgroup / InvalidRatio (.index = vector)."""
+    f = lib().ss_phase1_verification_ratios
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int,
+                  C.c_int, C.c_char_p]
+    pin, k1 = _buf(output)
+    pnc, k2 = _buf(new_challenge) if new_challenge is not None else (None, None)
+    _check(f(C.byref(params.c), pin, len(output), int(compressed_output), check_output, pnc,
+             len(new_challenge) if new_challenge is not None else 0, int(compressed_new_challenge), subgroup_mode,
+             bytes(seed) if seed is not None else None))
+
+
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
                        tau, alpha, beta):
     """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place."""

@@ -108,3 +108,49 @@ def test_power_pairs_feed_check_same_ratio(curve, power):
     with pytest.raises(S.InvalidRatio) as e:
         S.check_same_ratio_batch(cid, g1_pairs, g2_pairs)
     assert e.value.index == 2
+
+
+@pytest.mark.parametrize("curve,power", [("bls12_377", 12), ("bw6_761", 7)])
+def test_phase1_verification_ratios_verdicts(curve, power):
+    """verification.rs tests (:783-1106) accept a correct contribution and reject tampered ones; the verdict and
+    the failing vector must match what the reference reports (PointAtInfinity / IncorrectSubgroup / InvalidRatio)."""
+    cv, cid = R.CURVES[curve], CID[curve]
+    rp = R.Phase1Parameters(cv, power, 256)
+    sp = S.Phase1Parameters(cid, power, 256)
+    keys = [int.from_bytes(hashlib.blake2b(b"verd" + bytes([i]), digest_size=64).digest(), "little") % (cv.r - 2) + 2
+            for i in range(3)]
+    chal = bytearray(sp.get_length(False))
+    S.phase1_computation(sp, bytes(R.phase1_initialization(rp, False)), chal, False, False, S.CHECK_NO, *keys)
+    resp = bytearray(sp.get_length(True))
+    S.phase1_computation(sp, bytes(chal), resp, False, True, S.CHECK_NO, *[k + 1 for k in keys])
+    resp = bytes(resp)
+    newc = bytearray(sp.get_length(False))
+    seed = bytes(range(32))
+    S.phase1_verification_ratios(sp, resp, True, newc, False, seed=seed)
+    # the new challenge is the decompressed response
+    want = bytearray(sp.get_length(False))
+    S.phase1_computation(sp, bytes(chal), want, False, False, S.CHECK_NO, *[k + 1 for k in keys])
+    assert bytes(newc[64:]) == bytes(want[64:])
+    offs = rp.split_offsets(True)
+    c1, c2 = cv.g1.size(True), cv.g2.size(True)
+    # swap two adjacent elements in each vector in turn -> InvalidRatio on that vector
+    for vec, csz in ((0, c1), (1, c2), (2, c1), (3, c1)):
+        o = offs[vec][0]
+        bad = bytearray(resp)
+        bad[o + 5 * csz:o + 6 * csz], bad[o + 6 * csz:o + 7 * csz] = resp[o + 6 * csz:o + 7 * csz], resp[o + 5 * csz:o + 6 * csz]
+        with pytest.raises(S.InvalidRatio) as e:
+            S.phase1_verification_ratios(sp, bytes(bad), True, None, False, seed=seed)
+        assert e.value.index == vec
+    # one element replaced by the wrong power (tau_g1[9] <- tau_g1[8]) -> InvalidRatio on tau_g1
+    o = offs[0][0]
+    bad = bytearray(resp)
+    bad[o + 9 * c1:o + 10 * c1] = resp[o + 8 * c1:o + 9 * c1]
+    with pytest.raises(S.InvalidRatio) as e:
+        S.phase1_verification_ratios(sp, bytes(bad), True, None, False, seed=seed)
+    assert e.value.index == 0
+    # infinity in beta_g1 -> PointAtInfinity before any pairing
+    o = offs[3][0]
+    bad = bytearray(resp)
+    bad[o + 4 * c1:o + 5 * c1] = cv.g1.encode(None, True)
+    with pytest.raises(S.PointAtInfinity):
+        S.phase1_verification_ratios(sp, bytes(bad), True, None, False, seed=seed)

@@ -141,7 +141,34 @@ def prepare_phase2(curve, power):
                       "path": "host buffers through ss_groth16_params_new"}), flush=True)
 
 
+def pairing_latency(curve):
+    """Latency of the device check_same_ratio (one warp per check): 1 check and the 4 checks of a response."""
+    from snark_setup_b200 import ffi as F
+    cv = R.CURVES[curve]
+    cid = S.BLS12_377 if curve == "bls12_377" else S.BW6_761
+    g1, g2 = cv.g1, cv.g2
+    x = scalar(b"pair-x", cv.r)
+    p1 = g1.write_batch([g1.gen, g1.mul(g1.gen, x)], False)
+    p2 = g2.write_batch([g2.gen, g2.mul(g2.gen, x)], False)
+    S.check_same_ratio(cid, p1, p2)
+    t1 = best(lambda: S.check_same_ratio(cid, p1, p2))
+    t4 = best(lambda: S.check_same_ratio_batch(cid, p1 * 4, p2 * 4))
+    t32 = best(lambda: S.check_same_ratio_batch(cid, p1 * 32, p2 * 32))
+    F.profile_enable(True)
+    F.profile_reset()
+    S.check_same_ratio_batch(cid, p1 * 4, p2 * 4)
+    prof = {k: round(v["ms"], 3) for k, v in F.profile_read().items()}
+    F.profile_enable(False)
+    print(json.dumps({"bench": "check_same_ratio on device (reduced Tate pairing product, one warp per check)",
+                      "curve": curve, "one_check_ms": round(t1 * 1e3, 2), "four_checks_ms": round(t4 * 1e3, 2),
+                      "thirty_two_checks_ms": round(t32 * 1e3, 2), "kernels_ms": prof}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pairing":
+        pairing_latency("bls12_377")
+        pairing_latency("bw6_761")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prepare_phase2":
         prepare_phase2(sys.argv[2] if len(sys.argv) > 2 else "bls12_377", int(sys.argv[3]) if len(sys.argv) > 3 else 18)
         sys.exit(0)
