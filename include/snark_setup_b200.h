@@ -293,6 +293,21 @@ int ss_phase1_verification_ratios(const ss_phase1_params* p, const uint8_t* outp
                                   int check_output, uint8_t* new_challenge, size_t new_challenge_len,
                                   int compressed_new_challenge, int subgroup_mode, const uint8_t* rho_seed);
 
+/* -------------------------------------------------------------------------------------------- */
+/* phase-2 QAP evaluation                                                */
+/* -------------------------------------------------------------------------------------------- */
+/* dot_product_vec + normalize_batch — phase2/src/polynomial.rs:30-47,75-94:
+ *   out_v = sum_{e in [row_ptr[v], row_ptr[v+1])} coeffs[e] * bases[index[e]],   v < rows
+ * `bases`: n_bases serialized elements (the Lagrange coefficients of Groth16Params); the matrix is the
+ * per-variable list `xt_processed` of MPCParameters::process_matrix (phase2/src/parameters.rs:96-105) in CSR
+ * form: row_ptr[rows + 1], index[nnz] (constraint numbers), coeffs[nnz] canonical little-endian scalars.
+ * A row without entries gives the point at infinity, as the reference's empty sum does.  dot_product_ext
+ * (polynomial.rs:51-68) is the same call over the concatenation [beta_coeffs | alpha_coeffs | coeffs_g1] with
+ * the indices of bt / ct shifted by m / 2m.  An index >= n_bases => SS_ERR_INVALID_LENGTH (reference: panic). */
+int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_compressed, int check, size_t n_bases,
+                       const uint64_t* row_ptr, const uint32_t* index, const uint8_t* coeffs, size_t rows, uint8_t* out,
+                       int out_compressed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -934,3 +934,39 @@ def check_same_ratio(curve: Curve, g1_pair, g2_pair):
         raise InvalidRatio("zero")
     if not same_ratio(curve, g1_pair, g2_pair):
         raise InvalidRatio("wrong pairing")
+
+
+# ----------------------------------------------------------------------------------------------
+# phase-2 QAP evaluation (phase2/src/polynomial.rs:11-94) — SURVEY.md §8f rank 4
+# ----------------------------------------------------------------------------------------------
+def dot_product(group: Group, row, coeffs):
+    """phase2/src/polynomial.rs:80-94: sum of coeffs[ind].mul(coeff) over the (coeff, ind) entries of one row."""
+    acc = None
+    for c, ind in row:
+        acc = group.add(acc, group.mul(coeffs[ind], c % group.r))
+    return acc
+
+
+def dot_product_vec(group: Group, rows, coeffs):
+    """phase2/src/polynomial.rs:75-77 (+ the normalize_batch of eval, :41-45): one affine point per row."""
+    return [dot_product(group, row, coeffs) for row in rows]
+
+
+def process_matrix(xt, num_vars):
+    """MPCParameters::process_matrix (phase2/src/parameters.rs:96-105): constraint-major -> variable-major."""
+    out = [[] for _ in range(num_vars)]
+    for constraint_num, vars_ in enumerate(xt):
+        for coeff, var_index in vars_:
+            out[var_index].append((coeff, constraint_num))
+    return out
+
+
+def qap_eval(curve: Curve, coeffs_g1, coeffs_g2, alpha_coeffs_g1, beta_coeffs_g1, at, bt, ct, num_inputs):
+    """phase2/src/polynomial.rs:11-47 -> (a_g1, b_g1, b_g2, gamma_abc_g1, l)."""
+    g1, g2 = curve.g1, curve.g2
+    a_g1 = dot_product_vec(g1, at, coeffs_g1)
+    b_g1 = dot_product_vec(g1, bt, coeffs_g1)
+    b_g2 = dot_product_vec(g2, bt, coeffs_g2)
+    ext = [g1.add(g1.add(dot_product(g1, a, beta_coeffs_g1), dot_product(g1, b, alpha_coeffs_g1)),
+                  dot_product(g1, c, coeffs_g1)) for a, b, c in zip(at, bt, ct)]
+    return a_g1, b_g1, b_g2, ext[:num_inputs], ext[num_inputs:]

@@ -41,6 +41,7 @@ from .ffi import (  # noqa: F401
     phase1_verification_vectors,
     phase1_verification_vectors_dev,
     power_pairs,
+    qap_dot_product,
     generate_powers_of_tau,
     group_ifft,
     groth16_params_new,

@@ -29,6 +29,7 @@
 #include "fft.cuh"
 #include "msm.cuh"
 #include "pairing.cuh"
+#include "qap.cuh"
 
 namespace {
 
@@ -425,12 +426,17 @@ struct ScalarSetup {
     }
 };
 
-bool scalar_is_canonical(int curve, const uint8_t* s) {
-    // r for BLS12-377 (32 bytes) / BW6-761 (48 bytes), little-endian compare from the top
+// r for BLS12-377 (8 words) / BW6-761 (12 words), little-endian u32 limbs
+const uint32_t* scalar_modulus(int curve, int* n) {
     static const uint32_t r_bls[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
     static const uint32_t r_bw6[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
-    const uint32_t* r = curve == SS_CURVE_BLS12_377 ? r_bls : r_bw6;
-    int n = curve == SS_CURVE_BLS12_377 ? 8 : 12;
+    *n = curve == SS_CURVE_BLS12_377 ? 8 : 12;
+    return curve == SS_CURVE_BLS12_377 ? r_bls : r_bw6;
+}
+
+bool scalar_is_canonical(int curve, const uint8_t* s) {
+    int n;
+    const uint32_t* r = scalar_modulus(curve, &n);
     for (int i = n - 1; i >= 0; i--) {
         uint32_t w;
         memcpy(&w, s + 4 * i, 4);
@@ -1025,3 +1031,4 @@ int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, si
 
 #include "api_fft.inl"
 #include "api_pairing.inl"
+#include "api_qap.inl"

@@ -1,6 +1,7 @@
 // Kernel instantiations for Bls377G1 (one translation unit per group keeps nvcc compile times parallel).
 #include "fft.cuh"
 #include "msm.cuh"
+#include "qap.cuh"
 
 namespace ss {
 const GroupOps& ops_bls377_g1() {
@@ -13,6 +14,10 @@ const MsmOps& msm_ops_bls377_g1() {
 }
 const FftOps& fft_ops_bls377_g1() {
     static const FftOps o = FftLaunch<Bls377G1>::ops();
+    return o;
+}
+const QapOps& qap_ops_bls377_g1() {
+    static const QapOps o = QapLaunch<Bls377G1>::ops();
     return o;
 }
 }  // namespace ss

@@ -1,6 +1,7 @@
 // Kernel instantiations for Bw6G2 (one translation unit per group keeps nvcc compile times parallel).
 #include "fft.cuh"
 #include "msm.cuh"
+#include "qap.cuh"
 
 namespace ss {
 const GroupOps& ops_bw6_g2() {
@@ -13,6 +14,10 @@ const MsmOps& msm_ops_bw6_g2() {
 }
 const FftOps& fft_ops_bw6_g2() {
     static const FftOps o = FftLaunch<Bw6G2>::ops();
+    return o;
+}
+const QapOps& qap_ops_bw6_g2() {
+    static const QapOps o = QapLaunch<Bw6G2>::ops();
     return o;
 }
 }  // namespace ss

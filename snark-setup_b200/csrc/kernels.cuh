@@ -256,6 +256,7 @@ struct ScalarMulArgs {
     uint64_t power_mask = ~0ull;
     int src_log_m = -1;
     uint64_t coeff_limit = ~0ull;
+    const uint32_t* gather = nullptr;  // sparse dot products (qap.cuh): thread i multiplies aff[gather[i]]
 };
 
 // bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
@@ -275,6 +276,8 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
     if (a.src_log_m >= 0) {
         const uint64_t m = 1ull << a.src_log_m;
         src = ((i >> a.src_log_m) << (a.src_log_m + 1)) | m | (i & (m - 1));
+    } else if (a.gather) {
+        src = a.gather[i];
     }
     Affine<F> base = load_affine<G>(a.aff, a.inf, a.n, src);
     Fp<FrP> s;

@@ -503,6 +503,33 @@ def phase1_verification_ratios(params, output, compressed_output, new_challenge,
              bytes(seed) if seed is not None else None))
 
 
+def qap_dot_product(curve, group, bases, bases_compressed, rows, out_compressed, check=CHECK_NO):
+    """dot_product_vec + normalize_batch (phase2/src/polynomial.rs:30-47,75-94).  `rows` = per-variable lists
+    [(coeff, index), ...] as MPCParameters::process_matrix builds them (phase2/src/parameters.rs:96-105)."""
+    import array
+    f = lib().ss_qap_dot_product
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_size_t, C.c_void_p, C.c_int]
+    fb = scalar_size(curve)
+    n = len(bases) // element_size(curve, group, bases_compressed)
+    row_ptr = array.array("Q", [0])
+    index = array.array("I")
+    coeffs = bytearray()
+    for row in rows:
+        for c, i in row:
+            index.append(i)
+            coeffs += int(c).to_bytes(fb, "little")
+        row_ptr.append(len(index))
+    out = bytearray(max(1, len(rows)) * element_size(curve, group, out_compressed))
+    pb, k1 = _buf(bases) if n else (None, None)
+    po, k2 = _buf(out)
+    prp, k3 = _buf(bytearray(row_ptr.tobytes()))
+    pix, k4 = _buf(bytearray(index.tobytes())) if len(index) else (None, None)
+    pco, k5 = _buf(coeffs) if len(coeffs) else (None, None)
+    _check(f(curve, group, pb, int(bases_compressed), check, n, prp, pix, pco, len(rows), po, int(out_compressed)))
+    return bytes(out[:len(rows) * element_size(curve, group, out_compressed)])
+
+
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
                        tau, alpha, beta):
     """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place."""
