@@ -28,7 +28,7 @@ int log2_exact(uint64_t n) {
 // One vector: decode n + h_count elements (n = 2^log_n), optionally emit the H query
 // h_i = P_(i+n) - P_i for i < h_count, then the n Lagrange coefficients.  in/out/h_out are HOST buffers.
 int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int log_n, uint64_t h_count, uint8_t* out,
-               uint8_t* h_out, int out_c, const char* what) {
+               uint8_t* h_out, int out_c, const char* what, int device_slot = 0) {
     const GroupOps* op = group_ops(curve, group);
     const FftOps* fp = fft_ops(curve, group);
     if (!op || !fp) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group");
@@ -40,7 +40,7 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
     const FftOps& f = *fp;
     int rc = ensure_init();
     if (rc) return rc;
-    const int device = g_devices[0];
+    const int device = g_devices[(size_t)device_slot % g_devices.size()];
     const uint64_t n = 1ull << log_n, nd = n + h_count, half = n >> 1;
     const size_t isz = in_c ? o.csize : o.usize, osz = out_c ? o.csize : o.usize;
     const size_t cw = (size_t)o.coord_words * 4, frw = o.fr_words;
@@ -265,18 +265,42 @@ int ss_groth16_params_new(const ss_phase1_params* p, const uint8_t* accumulator,
     uint8_t* beta_g1 = alpha_g1 + m * o1;
     uint8_t* h_g1 = beta_g1 + m * o1;
     (void)i1;
-    if ((rc = fft_vector(p->curve, SS_G1, accumulator + off[0], compressed_input, check, lm, m - 1, coeffs_g1, h_g1,
-                         compressed_output, "tau_g1 coefficients")))
-        return rc;
-    if ((rc = fft_vector(p->curve, SS_G2, accumulator + off[1], compressed_input, check, lm, 0, coeffs_g2, nullptr,
-                         compressed_output, "tau_g2 coefficients")))
-        return rc;
-    if ((rc = fft_vector(p->curve, SS_G1, accumulator + off[2], compressed_input, check, lm, 0, alpha_g1, nullptr,
-                         compressed_output, "alpha_g1 coefficients")))
-        return rc;
-    if ((rc = fft_vector(p->curve, SS_G1, accumulator + off[3], compressed_input, check, lm, 0, beta_g1, nullptr,
-                         compressed_output, "beta_g1 coefficients")))
-        return rc;
+    // The four transforms are independent (the reference spawns one crossbeam thread each, groth16_utils.rs:103-111):
+    // one host thread + lane each, spread over the selected devices (ss_init / $SNARK_SETUP_GPUS) round-robin;
+    // on one device they overlap, so the low-occupancy normalisation tails of one hide behind another's
+    // scalar multiplications.  The heaviest (G2) goes first.
+    if ((rc = ensure_init())) return rc;
+    struct Job {
+        int group;
+        const uint8_t* in;
+        uint64_t h;
+        uint8_t* out;
+        uint8_t* h_out;
+        const char* what;
+    };
+    const Job jobs[4] = {{SS_G2, accumulator + off[1], 0, coeffs_g2, nullptr, "tau_g2 coefficients"},
+                         {SS_G1, accumulator + off[0], m - 1, coeffs_g1, h_g1, "tau_g1 coefficients"},
+                         {SS_G1, accumulator + off[2], 0, alpha_g1, nullptr, "alpha_g1 coefficients"},
+                         {SS_G1, accumulator + off[3], 0, beta_g1, nullptr, "beta_g1 coefficients"}};
+    int rcs[4] = {0, 0, 0, 0};
+    ss_error_info errs[4];
+    auto run = [&](int v) {
+        rcs[v] = fft_vector(p->curve, jobs[v].group, jobs[v].in, compressed_input, check, lm, jobs[v].h, jobs[v].out,
+                            jobs[v].h_out, compressed_output, jobs[v].what, v);
+        if (rcs[v]) errs[v] = g_err;
+    };
+    if (concurrent_vectors()) {
+        std::vector<std::thread> th;
+        for (int v = 0; v < 4; v++) th.emplace_back(run, v);
+        for (auto& t : th) t.join();
+    } else {
+        for (int v = 0; v < 4; v++) run(v);
+    }
+    for (int v = 0; v < 4; v++)
+        if (rcs[v]) {
+            g_err = errs[v];
+            return rcs[v];
+        }
     return SS_OK;
 }
 

@@ -51,3 +51,28 @@ def test_two_devices_one_call():
         assert verdicts == [True, True, True, False]
     finally:
         ffi.init([0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_prepare_phase2_over_two_devices():
+    """Groth16Params::new spreads its four transforms over the selected devices; bytes must not depend on that."""
+    cv, cid = R.BLS12_377, S.BLS12_377
+    power = 6
+    rp = R.Phase1Parameters(cv, power, 64)
+    sp = S.Phase1Parameters(cid, power, 64)
+    keys = [random.Random(5).randrange(2, cv.r) for _ in range(3)]
+    acc = bytearray(sp.get_length(False))
+    S.phase1_computation(sp, bytes(R.phase1_initialization(rp, False)), acc, False, False, S.CHECK_NO, *keys)
+    one = S.groth16_params_new(sp, bytes(acc), False, 1 << power, True)
+    try:
+        ffi.init([0, 1])
+        two = S.groth16_params_new(sp, bytes(acc), False, 1 << power, True)
+    finally:
+        ffi.init([0])
+    assert one == two
+    # against the oracle on the first coefficients vector
+    s1c, s2c = cv.g1.size(True), cv.g2.size(True)
+    offs = rp.split_offsets(False)
+    tau_g1 = cv.g1.read_batch(bytes(acc[offs[0][0]:offs[0][0] + (1 << power) * cv.g1.size(False)]), False)
+    want = cv.g1.write_batch(R.group_ifft_fast(cv.g1, tau_g1), True)
+    assert one[2 * s1c + s2c:2 * s1c + s2c + (1 << power) * s1c] == want
