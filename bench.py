@@ -114,6 +114,7 @@ def run_reference(args, rank):
     total = sum(times)
     v = (1 << k) * len(times) / total
     sample = f"2^{k}-power BLS12-377 Phase1::computation (uncompressed in, compressed out) per step"
+    restore_stdout()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "powers/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -149,6 +150,18 @@ def cpu_baseline(budget_s=12.0):
             "sample": f"one 2^{k}-power BLS12-377 Phase1::computation pass ({dt:.2f} s); linear in powers"}
 
 
+_STDOUT_FD = None
+
+
+def restore_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is not None:
+        sys.stdout.flush()
+        os.dup2(_STDOUT_FD, 1)
+        os.close(_STDOUT_FD)
+        _STDOUT_FD = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +176,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries the ONE JSON line and nothing else: anything native libraries write to fd 1 while the
+    # bench runs (NCCL prints its version line there when NCCL_DEBUG=VERSION) is sent to stderr instead.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -180,8 +199,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default; stdout carries the ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ffi.init([local_rank])
 
@@ -376,6 +393,7 @@ def main():
         cpu = cpu_baseline()
 
     if rank == 0:
+        restore_stdout()
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "powers/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",

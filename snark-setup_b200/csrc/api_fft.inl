@@ -87,7 +87,8 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
         na.prefix = prefix;
         na.out = reinterpret_cast<uint32_t*>(bytes_out);
         na.out_compressed = out_c;
-        na.threads = normalize_threads(cnt);
+        // mid-size transforms: more, shorter batch inversions (n/32 threads would leave most SMs idle)
+        na.threads = std::max<uint32_t>(normalize_threads(cnt), (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cnt / 4, 1), 32768));
         if (!bytes_out) {
             na.aff_out = aff;
             na.inf_out = inf;
