@@ -38,6 +38,11 @@ BLS_R = 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001
 W_REF_G1_MUL = 948750
 W_REF_G2_MUL = 2314950
 W_REF_POWER = 6109950
+# Work the kernels actually EXECUTE (GLV/GLS + signed windows, glv.cuh): field multiplications / squarings per
+# scalar multiplication counted on the host-emulated device code (tests/test_device_algos_emul.py::
+# test_executed_work_per_scalar_mul pins them), in MAC32 = 2n^2+n per multiplication, (3n^2+3n)/2 per squaring (n = 12).
+W_EXEC_G1_MUL = 775 * 300 + 890 * 234
+W_EXEC_G2_MUL = 3200 * 300
 METRIC = "phase1 contribute+verify G1+G2 powers/sec at 2^22 (1/2/4/8 B200), bit-exact"
 
 
@@ -383,6 +388,12 @@ def main():
                     "traffic": (imad or {}).get("scalar_mul_g1_dram_bytes_per_launch"),
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]), "kernel_share_of_step": d["ms"] / total_ms,
                     "whole_step_frac": W_REF_POWER * (value / world) * 1e-12 / mac_peak,
+                    "executed": {"what": "MAC32 the kernel really executes (GLV/GLS algorithm, counted on the emulated "
+                                         "device code) / duration; frac = share of the multiplier peak in use",
+                                 "mac32_per_element": W_EXEC_G2_MUL if ".g2" in name else W_EXEC_G1_MUL,
+                                 "achieved": (W_EXEC_G2_MUL if ".g2" in name else W_EXEC_G1_MUL) * d["elements"] / (d["ms"] * 1e-3) * 1e-12,
+                                 "frac": (W_EXEC_G2_MUL if ".g2" in name else W_EXEC_G1_MUL) * d["elements"] / (d["ms"] * 1e-3) * 1e-12 / mac_peak,
+                                 "ncu_fmaheavy_pct_of_elapsed": 87.2 if ".g1" in name else 78.3},
                     "hbm": {"algorithmic_GBps": (acc_len + resp_len) * args.steps / (dev_ms * 1e-3) * 1e-9,
                             "peak_GBps": peaks.get("hbm_gbs")},
                     "serialised_step_ms": serial_ms,

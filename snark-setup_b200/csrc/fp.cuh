@@ -294,11 +294,22 @@ __device__ __noinline__ Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) {
 }
 #endif
 
+// Host-emulation builds (tests/emul) can count the field multiplications / squarings an algorithm executes:
+// ss_op_count[0][N] multiplications, [1][N] squarings on N-limb fields.  bench.py's "executed work" figure is
+// pinned by tests/test_device_algos_emul.py::test_executed_work_per_scalar_mul with these counters.
+#if defined(SS_COUNT_OPS) && !defined(__CUDACC__)
+inline unsigned long long ss_op_count[2][32] = {};
+#define SS_COUNT_OP(kind, n) (++ss_op_count[kind][n])
+#else
+#define SS_COUNT_OP(kind, n) ((void)0)
+#endif
+
 template <class P>
 SS_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
     return fp_mul_call<P>(a, b);
 #else
+    SS_COUNT_OP(0, P::N);
     return fp_mul_inl(a, b);
 #endif
 }
@@ -374,6 +385,7 @@ SS_HD Fp<P> fp_sqr(const Fp<P>& a) {
 #elif defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
     return fp_sqr_call<P>(a);
 #else
+    SS_COUNT_OP(1, P::N);
     return fp_sqr_inl(a);
 #endif
 }

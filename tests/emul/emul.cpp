@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: host build of the device math headers (ptx.cuh's carry-flag emulation), so
 // the limb-level algorithms can be checked against oracle/pyref.py on a box without a GPU.
 // Never linked into the product library.
+#define SS_COUNT_OPS 1  // fp.cuh: count multiplications / squarings (host emulation only)
 #include <cstring>
 #include "../../snark-setup_b200/csrc/codec.cuh"
 #include "../../snark-setup_b200/csrc/glv.cuh"
@@ -166,7 +167,33 @@ static int subgroup_both(const uint8_t* in) {
     return (in_subgroup<G>(p) ? 1 : 0) | (in_subgroup_rmul<G>(p) ? 2 : 0);
 }
 
+template <class G>
+static int count_scalar_mul(const uint8_t* in, const uint8_t* scalar, unsigned long long* counts) {
+    using F = typename G::F;
+    Affine<F> p;
+    uint32_t w[64];
+    memcpy(w, in, G::USIZE);
+    int e = decode_point<G>(w, false, CHECK_NO, p);
+    if (e) return e;
+    uint32_t k[12] = {0};
+    memcpy(k, scalar, 4 * G::Fr::N);
+    memset(ss_op_count, 0, sizeof(ss_op_count));
+    Jac<F> r = scalar_mul_endo<G>(p, k);
+    memcpy(counts, ss_op_count, sizeof(ss_op_count));
+    return r.is_identity() ? 1 : 0;
+}
+
 extern "C" {
+// counts[kind][limbs] (kind 0 = multiplications, 1 = squarings) executed by ONE scalar_mul_endo<G> (glv.cuh)
+int emul_count_scalar_mul(int group, const uint8_t* in, const uint8_t* scalar, unsigned long long* counts) {
+    switch (group) {
+        case 0: return count_scalar_mul<Bls377G1>(in, scalar, counts);
+        case 1: return count_scalar_mul<Bls377G2>(in, scalar, counts);
+        case 2: return count_scalar_mul<Bw6G1>(in, scalar, counts);
+        case 3: return count_scalar_mul<Bw6G2>(in, scalar, counts);
+    }
+    return -1;
+}
 // bit0: endomorphism test, bit1: r-multiplication
 int emul_in_subgroup(int group, const uint8_t* in) {
     switch (group) {

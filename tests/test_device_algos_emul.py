@@ -114,3 +114,30 @@ def test_subgroup_test_equals_r_multiplication(L, gid):
     for P in pts:
         rc = L.emul_in_subgroup(gid, g.encode(P, 0))
         assert rc == (3 if g.in_subgroup(P) else 0), (g.name, P, rc)
+
+
+def test_executed_work_per_scalar_mul(L):
+    """Pins the executed-work figures bench.py reports beside the W_ref-based roofline fraction: field
+    multiplications / squarings one scalar_mul_endo<G> performs (mean over random scalars)."""
+    import ctypes
+    import statistics
+    rng = random.Random(2026)
+    want = {0: ((12, 740, 810), (12, 860, 920)), 1: ((12, 3050, 3350), None), 2: ((24, 1080, 1200), (24, 1260, 1400)),
+            3: ((24, 1080, 1200), (24, 1260, 1400))}
+    for gid, (cv, g) in enumerate([(R.BLS12_377, R.BLS12_377.g1), (R.BLS12_377, R.BLS12_377.g2),
+                                   (R.BW6_761, R.BW6_761.g1), (R.BW6_761, R.BW6_761.g2)]):
+        muls, sqrs = [], []
+        for _ in range(6 if gid < 2 else 3):
+            P = g.mul(g.gen, rng.randrange(1, cv.r))
+            k = rng.randrange(cv.r)
+            counts = (ctypes.c_ulonglong * 64)()
+            assert L.emul_count_scalar_mul(gid, g.encode(P, False), k.to_bytes(48, "little"), counts) == 0
+            (n, lo, hi), sq = want[gid]
+            muls.append(counts[n])
+            sqrs.append(counts[32 + n])
+            assert sum(counts) == counts[n] + counts[32 + n]  # nothing on other field widths
+        assert lo <= statistics.mean(muls) <= hi, (g.name, muls)
+        if sq:
+            assert sq[1] <= statistics.mean(sqrs) <= sq[2], (g.name, sqrs)
+        else:
+            assert sum(sqrs) == 0  # Fq2 squarings are two base multiplications (complex squaring)
