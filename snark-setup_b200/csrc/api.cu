@@ -6,7 +6,7 @@
 //   apply_powers                          phase1/src/helpers/buffers.rs:77-97
 //   Phase1::computation (Groth16)         phase1/src/computation.rs:40-193
 // The reference walks each vector in `batch_size` windows on rayon threads; results do not depend
-// on the windowing, so here each vector is cut into device tiles (default 2^18 elements) that are
+// on the windowing, so here each vector is cut into device tiles (default 606 208 elements) that are
 // pipelined over two CUDA streams (H2D of tile k+1 overlaps the kernels of tile k), the five vectors
 // of a call run on concurrent lanes, and with several devices every vector is split D ways.
 #ifndef __CUDACC__
@@ -185,13 +185,23 @@ bool concurrent_vectors() {
     return v != 0;
 }
 
+// Elements per device tile.  k_scalar_mul does the same work in every thread, so its blocks finish in waves:
+// the default is 8 whole waves of the G1 kernel (148 SMs x 4 resident blocks x 128 threads = 75 776
+// elements per wave; the G2 kernel's waves are half that).  Measured (profiles/r01_ab_variants.md): wave quantisation is
+// NOT visible (2^18: 251 ms, 4 waves: 248 ms), larger tiles win 1.3 % through fewer normalisation tails.  $SS_TILE_ELEMS / $SS_TILE_LOG2 override.
 size_t tile_elems() {
     static size_t t = [] {
-        const char* e = getenv("SS_TILE_LOG2");
-        int l = e ? atoi(e) : 18;
-        if (l < 8) l = 8;
-        if (l > 24) l = 24;
-        return (size_t)1 << l;
+        if (const char* e = getenv("SS_TILE_ELEMS")) {
+            long long v = atoll(e);
+            if (v >= 256 && v <= (1ll << 24)) return (size_t)v;
+        }
+        if (const char* e = getenv("SS_TILE_LOG2")) {
+            int l = atoi(e);
+            if (l < 8) l = 8;
+            if (l > 24) l = 24;
+            return (size_t)1 << l;
+        }
+        return (size_t)8 * 75776;
     }();
     return t;
 }
