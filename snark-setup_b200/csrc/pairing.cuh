@@ -17,6 +17,11 @@
 //   * Final exponentiation: f^(q^(k/2)-1) = conj(f)/f (norm to the cubic subfield, one F inversion), then
 //     f^(Q+1) with Q = q^2 (k = 12) / q (k = 6) through the Frobenius multipliers zeta^k (in Fq), then the
 //     hard part Phi_k(q)/r by square-and-multiply (1255 / 1144 bits; exponent from tools/gen_constants.py).
+//   * BLS12-377 takes two shortcuts with the same verdict (Bls377Pairing::ATE / FROB4): the Miller loop is the ate loop
+//     over u (64 bits, Miller points on the twist over Fq2, lines at positions 1, w, w^3 — see miller_ate) instead of
+//     the Tate loop over r (253 bits), and the hard part is a 4-way simultaneous exponentiation over the base-q
+//     digits of the exponent (314 bits: f^(q^i) by the q-power Frobenius c_k -> conj(c_k) gamma^k).  BW6-761 keeps
+//     the plain forms.
 // O(1) work per verification (4 checks per response): latency, not throughput, is what matters here.
 #pragma once
 #include "codec.cuh"
@@ -51,6 +56,8 @@ struct Bls377Pairing {
     using PP = Bls377PairingParams;
     static constexpr int XPOS = 2;               // D-type: x_Q = x' w^2, y_Q = y' w^3
     static constexpr bool XI_ON_CONST = false;
+    static constexpr bool ATE = true;            // Miller loop over u on the twist (64 bits) instead of r on G1 (253)
+    static constexpr bool FROB4 = true;          // hard part as a 4-way simultaneous exponentiation over f^(q^i)
     SS_D static F mul_xi(const F& a) { return F{fp_neg(fp_mul5(a.c1)), a.c0}; }  // xi = u, u^2 = -5
 };
 struct Bw6Pairing {
@@ -61,6 +68,8 @@ struct Bw6Pairing {
     using PP = Bw6PairingParams;
     static constexpr int XPOS = 4;               // M-type: xi x_Q = x' w^4, xi y_Q = y' w^3 (whole line scaled by xi)
     static constexpr bool XI_ON_CONST = true;
+    static constexpr bool ATE = false;
+    static constexpr bool FROB4 = false;
     SS_D static F mul_xi(const F& a) { return fp_neg(fp_dbl(fp_dbl(a))); }  // xi = -4
 };
 
@@ -105,6 +114,129 @@ SS_D typename C::F ext_mul_line(const typename C::F& f, const typename C::Fq& s0
     return c;
 }
 
+// f * (c0 + c1 w + c3 w^3), all three in F — the lines of the ate Miller loop on a D-type twist
+template <class C>
+SS_D typename C::F ext_mul_013(const typename C::F& f, const typename C::F& c0, const typename C::F& c1,
+                               const typename C::F& c3, int k) {
+    using F = typename C::F;
+    F c = fp_mul(f, c0);
+    {
+        int j = k - 1;
+        const bool wrap = j < 0;
+        if (wrap) j += 6;
+        F t = fp_mul(lane_get(f, j), c1);
+        c = fp_add(c, wrap ? C::mul_xi(t) : t);
+    }
+    {
+        int j = k - 3;
+        const bool wrap = j < 0;
+        if (wrap) j += 6;
+        F t = fp_mul(lane_get(f, j), c3);
+        c = fp_add(c, wrap ? C::mul_xi(t) : t);
+    }
+    return c;
+}
+
+// Tate: f_{r,P0}(psi Q0) * f_{r,P1}(psi Q1), Miller points on G1 (see the header of this file for the lines)
+template <class C>
+SS_D typename C::F miller_tate(const Affine<typename C::Fq>* P, const Affine<typename C::F>* Q, int k) {
+    using F = typename C::F;
+    using Fq = typename C::Fq;
+    using G1 = typename C::G1;
+    Jac<Fq> T[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) T[j] = Jac<Fq>{P[j].x, P[j].y, Fq::one()};
+    F f = k == 0 ? F::one() : F::zero();
+#pragma unroll 1
+    for (int i = G1::GP::ORDER_BITS - 2; i >= 0; i--) {
+        f = ext_mul<C>(f, f, k);
+#pragma unroll 1
+        for (int j = 0; j < 2; j++) {
+            const Jac<Fq>& t = T[j];
+            Fq X2 = fp_sqr(t.X), Y2 = fp_sqr(t.Y), Z2 = fp_sqr(t.Z);
+            Fq X2_3 = fp_add(fp_dbl(X2), X2);
+            Fq s0 = fp_sub(fp_mul(X2_3, t.X), fp_dbl(Y2));
+            Fq sx = fp_neg(fp_mul(X2_3, Z2));
+            Fq sy = fp_dbl(fp_mul(fp_mul(t.Y, t.Z), Z2));
+            f = ext_mul_line<C>(f, s0, fscale(Q[j].x, sx), fscale(Q[j].y, sy), k);
+            T[j] = jac_dbl(t);
+        }
+        const bool bit = (G1::GP::order(i >> 5) >> (i & 31)) & 1;
+        if (bit && i != 0) {  // the last addition (T = -P) is a vertical line
+#pragma unroll 1
+            for (int j = 0; j < 2; j++) {
+                const Jac<Fq>& t = T[j];
+                Fq Z2 = fp_sqr(t.Z);
+                Fq N = fp_sub(t.Y, fp_mul(P[j].y, fp_mul(Z2, t.Z)));
+                Fq D = fp_mul(t.Z, fp_sub(t.X, fp_mul(P[j].x, Z2)));
+                Fq s0 = fp_sub(fp_mul(N, P[j].x), fp_mul(D, P[j].y));
+                f = ext_mul_line<C>(f, s0, fscale(Q[j].x, fp_neg(N)), fscale(Q[j].y, D), k);
+                T[j] = jac_madd(t, P[j]);
+            }
+        }
+    }
+    return f;
+}
+
+// ate (BLS12, D-type twist): f_{u,Q0}(P0) * f_{u,Q1}(P1), Miller points T on the twist E'(Fq2), lines evaluated
+// at P in E(Fq) and scaled by Fq2 factors:
+//   tangent at T = (X, Y, Z):  2YZ^3 y_P  -  3X^2 Z^2 x_P * w  +  (3X^3 - 2Y^2) * w^3
+//   chord through T and Q:     D y_P      -  N x_P * w         +  (N x_Q - D y_Q) * w^3,  N = Y - y_Q Z^3, D = Z (X - x_Q Z^2)
+template <class C>
+SS_D typename C::F miller_ate(const Affine<typename C::Fq>* P, const Affine<typename C::F>* Q, int k) {
+    using F = typename C::F;
+    using PP = typename C::PP;
+    Jac<F> T[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) T[j] = Jac<F>{Q[j].x, Q[j].y, F::one()};
+    F f = k == 0 ? F::one() : F::zero();
+#pragma unroll 1
+    for (int i = PP::ATE_BITS - 2; i >= 0; i--) {
+        f = ext_mul<C>(f, f, k);
+#pragma unroll 1
+        for (int j = 0; j < 2; j++) {
+            const Jac<F>& t = T[j];
+            F X2 = fp_sqr(t.X), Y2 = fp_sqr(t.Y), Z2 = fp_sqr(t.Z);
+            F X2_3 = fp_add(fp_dbl(X2), X2);
+            F c3 = fp_sub(fp_mul(X2_3, t.X), fp_dbl(Y2));
+            F c1 = fscale(fp_neg(fp_mul(X2_3, Z2)), P[j].x);
+            F c0 = fscale(fp_dbl(fp_mul(fp_mul(t.Y, t.Z), Z2)), P[j].y);
+            f = ext_mul_013<C>(f, c0, c1, c3, k);
+            T[j] = jac_dbl(t);
+        }
+        if ((PP::ate(i >> 5) >> (i & 31)) & 1) {
+#pragma unroll 1
+            for (int j = 0; j < 2; j++) {
+                const Jac<F>& t = T[j];
+                F Z2 = fp_sqr(t.Z);
+                F N = fp_sub(t.Y, fp_mul(Q[j].y, fp_mul(Z2, t.Z)));
+                F D = fp_mul(t.Z, fp_sub(t.X, fp_mul(Q[j].x, Z2)));
+                F c3 = fp_sub(fp_mul(N, Q[j].x), fp_mul(D, Q[j].y));
+                f = ext_mul_013<C>(f, fscale(D, P[j].y), fscale(fp_neg(N), P[j].x), c3, k);
+                T[j] = jac_madd(t, Q[j]);
+            }
+        }
+    }
+    return f;
+}
+
+// q-power Frobenius on the w-basis over Fq2: c_k -> conj(c_k) * gamma^k
+template <class C, class P>
+SS_D Fp2<P> frobenius_q(const Fp2<P>& c, int k) {
+    using PP = typename C::PP;
+    Fp2<P> g;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) {
+        g.c0.l[i] = PP::frobq(k, i);
+        g.c1.l[i] = PP::frobq(k, P::N + i);
+    }
+    return fp_mul(Fp2<P>{c.c0, fp_neg(c.c1)}, g);
+}
+template <class C, class P>
+SS_D Fp<P> frobenius_q(const Fp<P>& c, int) {
+    return c;  // not used (FROB4 is an Fq2-tower option)
+}
+
 // verdict bits: 1 = same ratio, 2 = one of the four points is the identity (check_same_ratio rejects those)
 template <class C>
 __global__ void __launch_bounds__(32) k_same_ratio(const uint32_t* g1_pairs, const uint32_t* g2_pairs, int count,
@@ -140,38 +272,9 @@ __global__ void __launch_bounds__(32) k_same_ratio(const uint32_t* g1_pairs, con
         P[1] = affine_neg(a1);
         Q[1] = b0;
     }
-    Jac<Fq> T[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) T[j] = Jac<Fq>{P[j].x, P[j].y, Fq::one()};
-    F f = k == 0 ? F::one() : F::zero();
-#pragma unroll 1
-    for (int i = G1::GP::ORDER_BITS - 2; i >= 0; i--) {
-        f = ext_mul<C>(f, f, k);
-#pragma unroll 1
-        for (int j = 0; j < 2; j++) {
-            const Jac<Fq>& t = T[j];
-            Fq X2 = fp_sqr(t.X), Y2 = fp_sqr(t.Y), Z2 = fp_sqr(t.Z);
-            Fq X2_3 = fp_add(fp_dbl(X2), X2);
-            Fq s0 = fp_sub(fp_mul(X2_3, t.X), fp_dbl(Y2));
-            Fq sx = fp_neg(fp_mul(X2_3, Z2));
-            Fq sy = fp_dbl(fp_mul(fp_mul(t.Y, t.Z), Z2));
-            f = ext_mul_line<C>(f, s0, fscale(Q[j].x, sx), fscale(Q[j].y, sy), k);
-            T[j] = jac_dbl(t);
-        }
-        const bool bit = (G1::GP::order(i >> 5) >> (i & 31)) & 1;
-        if (bit && i != 0) {  // the last addition (T = -P) is a vertical line
-#pragma unroll 1
-            for (int j = 0; j < 2; j++) {
-                const Jac<Fq>& t = T[j];
-                Fq Z2 = fp_sqr(t.Z);
-                Fq N = fp_sub(t.Y, fp_mul(P[j].y, fp_mul(Z2, t.Z)));
-                Fq D = fp_mul(t.Z, fp_sub(t.X, fp_mul(P[j].x, Z2)));
-                Fq s0 = fp_sub(fp_mul(N, P[j].x), fp_mul(D, P[j].y));
-                f = ext_mul_line<C>(f, s0, fscale(Q[j].x, fp_neg(N)), fscale(Q[j].y, D), k);
-                T[j] = jac_madd(t, P[j]);
-            }
-        }
-    }
+    F f;
+    if constexpr (C::ATE) f = miller_ate<C>(P, Q, k);
+    else f = miller_tate<C>(P, Q, k);
     // ---- final exponentiation ----
     F fc = (k & 1) ? fp_neg(f) : f;  // f^(q^(k/2)): w -> -w
     F nrm = ext_mul<C>(f, fc, k);    // in the cubic subfield F[v]/(v^3 - xi), v = w^2: coefficients 0, 2, 4
@@ -188,11 +291,36 @@ __global__ void __launch_bounds__(32) k_same_ratio(const uint32_t* g1_pairs, con
 #pragma unroll
     for (int i = 0; i < Fq::N; i++) z.l[i] = PP::frob(k, i);
     F f2 = ext_mul<C>(fscale(f1, z), f1, k);  // f1^(Q + 1): (sum c_k w^k)^Q = sum c_k zeta^k w^k
-    F acc = f2;
+    F acc;
+    if constexpr (C::FROB4) {
+        // hard = sum_i h_i q^i (i < 4): f2^hard = prod_i (f2^(q^i))^(h_i), one squaring and at most one table
+        // multiplication per bit of the (<= 314-bit) digits; tab[m] = prod_{i in m} f2^(q^i)
+        F tab[16];
+        tab[1] = f2;
+        tab[2] = frobenius_q<C>(tab[1], k);
+        tab[4] = frobenius_q<C>(tab[2], k);
+        tab[8] = frobenius_q<C>(tab[4], k);
+        tab[3] = ext_mul<C>(tab[1], tab[2], k);
 #pragma unroll 1
-    for (int i = PP::HARD_BITS - 2; i >= 0; i--) {
-        acc = ext_mul<C>(acc, acc, k);
-        if ((PP::hard(i >> 5) >> (i & 31)) & 1) acc = ext_mul<C>(acc, f2, k);
+        for (int m = 5; m < 8; m++) tab[m] = ext_mul<C>(tab[4], tab[m - 4], k);
+#pragma unroll 1
+        for (int m = 9; m < 16; m++) tab[m] = ext_mul<C>(tab[8], tab[m - 8], k);
+        acc = k == 0 ? F::one() : F::zero();
+#pragma unroll 1
+        for (int i = PP::HARDQ_BITS - 1; i >= 0; i--) {
+            acc = ext_mul<C>(acc, acc, k);
+            int m = 0;
+#pragma unroll
+            for (int d = 0; d < 4; d++) m |= (int)((PP::hardq(d, i >> 5) >> (i & 31)) & 1) << d;
+            if (m) acc = ext_mul<C>(acc, tab[m], k);
+        }
+    } else {
+        acc = f2;
+#pragma unroll 1
+        for (int i = PP::HARD_BITS - 2; i >= 0; i--) {
+            acc = ext_mul<C>(acc, acc, k);
+            if ((PP::hard(i >> 5) >> (i & 31)) & 1) acc = ext_mul<C>(acc, f2, k);
+        }
     }
     const bool ok = k == 0 ? (acc == F::one()) : acc.is_zero();
     const bool all_ok = __all_sync(0xffffffffu, ok);

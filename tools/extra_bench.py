@@ -159,7 +159,7 @@ def pairing_latency(curve):
     S.check_same_ratio_batch(cid, p1 * 4, p2 * 4)
     prof = {k: round(v["ms"], 3) for k, v in F.profile_read().items()}
     F.profile_enable(False)
-    print(json.dumps({"bench": "check_same_ratio on device (reduced Tate pairing product, one warp per check)",
+    print(json.dumps({"bench": "check_same_ratio on device (reduced pairing product, one warp per check)",
                       "curve": curve, "one_check_ms": round(t1 * 1e3, 2), "four_checks_ms": round(t4 * 1e3, 2),
                       "thirty_two_checks_ms": round(t32 * 1e3, 2), "kernels_ms": prof}), flush=True)
 
