@@ -84,8 +84,8 @@ int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_com
     const size_t need = 256 + align_up(isz * nb, 256) + align_up(2 * cw * nb, 256) + align_up(nb, 256) + align_up(4 * max_ent, 256) +
                         align_up(max_ent, 256) + align_up(8 * (max_seg + 1), 256) + align_up(8 * (max_rows + 1), 256) +
                         align_up(4 * max_gen, 256) + align_up(fb * max_gen, 256) + align_up(3 * cw * max_gen, 256) +
-                        align_up(3 * cw * max_seg, 256) + align_up(3 * cw * max_rows, 256) + align_up(cw * max_rows, 256) +
-                        align_up(osz * max_rows, 256);
+                        2 * align_up(3 * cw * max_seg, 256) + align_up(8 * (max_seg + 1), 256) + align_up(3 * cw * max_rows, 256) +
+                        align_up(cw * max_rows, 256) + align_up(osz * max_rows, 256);
     LaneGuard lg;
     if ((rc = lane_acquire(device, need, &lg.l))) return rc;
     cudaStream_t s = lg.l->stream;
@@ -102,6 +102,8 @@ int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_com
     uint8_t* d_gcoeff = cv.take<uint8_t>(fb * max_gen);
     uint32_t* jac_g = cv.take<uint32_t>(3 * cw * max_gen);
     uint32_t* partial = cv.take<uint32_t>(3 * cw * max_seg);
+    uint32_t* partial2 = cv.take<uint32_t>(3 * cw * max_seg);
+    uint64_t* d_seg2 = cv.take<uint64_t>(8 * (max_seg + 1));
     uint32_t* jac_rows = cv.take<uint32_t>(3 * cw * max_rows);
     uint32_t* prefix = cv.take<uint32_t>(cw * max_rows);
     uint8_t* d_out = cv.take<uint8_t>(osz * max_rows);
@@ -121,7 +123,7 @@ int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_com
         return rc;
     }
     std::vector<uint32_t> h_index, h_gather;
-    std::vector<uint64_t> h_seg, h_rowseg;
+    std::vector<uint64_t> h_seg, h_seg2, h_rowseg2;
     std::vector<uint8_t> h_gcoeff;
     for (const QapBlock& b : blocks) {
         const uint64_t ne = b.ent1 - b.ent0, nr = b.row1 - b.row0;
@@ -129,12 +131,18 @@ int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_com
         h_gather.clear();
         h_gcoeff.clear();
         h_seg.clear();
-        h_rowseg.clear();
+        // two levels of segments: entries -> partial sums of <= 256 entries -> partial sums of <= 256 partials
+        // -> row sums (a row of 2^24 entries is still only 256 additions deep at every level)
+        h_seg2.clear();
+        h_rowseg2.clear();
         for (uint64_t v = b.row0; v < b.row1; v++) {
-            h_rowseg.push_back(h_seg.size());
+            const uint64_t first_seg = h_seg.size();
             for (uint64_t e = row_ptr[v]; e < row_ptr[v + 1]; e += QAP_SEGMENT) h_seg.push_back(e - b.ent0);
+            h_rowseg2.push_back(h_seg2.size());
+            for (uint64_t sg = first_seg; sg < h_seg.size(); sg += QAP_SEGMENT) h_seg2.push_back(sg);
         }
-        h_rowseg.push_back(h_seg.size());
+        h_rowseg2.push_back(h_seg2.size());
+        h_seg2.push_back(h_seg.size());
         h_seg.push_back(ne);
         for (uint64_t e = b.ent0; e < b.ent1; e++) {
             if (kind[e] == 2) {
@@ -150,8 +158,10 @@ int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_com
             CU(cudaMemcpyAsync(d_index, h_index.data(), 4 * ne, cudaMemcpyHostToDevice, s));
             CU(cudaMemcpyAsync(d_kind, kind.data() + b.ent0, ne, cudaMemcpyHostToDevice, s));
         }
+        const uint64_t nseg2 = h_seg2.size() - 1;
         CU(cudaMemcpyAsync(d_seg, h_seg.data(), 8 * (nseg + 1), cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(d_rowseg, h_rowseg.data(), 8 * (nr + 1), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_seg2, h_seg2.data(), 8 * (nseg2 + 1), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(d_rowseg, h_rowseg2.data(), 8 * (nr + 1), cudaMemcpyHostToDevice, s));
         if (ng) {
             CU(cudaMemcpyAsync(d_gather, h_gather.data(), 4 * ng, cudaMemcpyHostToDevice, s));
             CU(cudaMemcpyAsync(d_gcoeff, h_gcoeff.data(), fb * ng, cudaMemcpyHostToDevice, s));
@@ -171,7 +181,8 @@ int ss_qap_dot_product(int curve, int group, const uint8_t* bases, int bases_com
         }
         QapSegArgs qa = {aff, inf, d_index, d_kind, d_seg, nseg, jac_g, std::max<uint64_t>(ng, 1), partial};
         { ProfScope ps("k_qap_segment_sum", o.name, ne, s); qp->segment_sum(qa, s); }
-        { ProfScope ps("k_qap_row_sum", o.name, nr, s); qp->row_sum(partial, nseg, d_rowseg, nr, jac_rows, s); }
+        { ProfScope ps("k_qap_row_sum", o.name, nseg2, s); qp->row_sum(partial, nseg, d_seg2, nseg2, partial2, s); }
+        { ProfScope ps("k_qap_row_sum", o.name, nr, s); qp->row_sum(partial2, nseg2, d_rowseg, nr, jac_rows, s); }
         NormalizeArgs na;
         na.jac = jac_rows;
         na.n = nr;

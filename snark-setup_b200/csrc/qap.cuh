@@ -6,8 +6,9 @@
 // into unit entries (a mixed addition of +-bases[index] straight from the decoded affine scratch) and general
 // entries (one gathered k_scalar_mul pass over the compacted list, GLV/GLS), and the sums are formed in two
 // passes so that a row with millions of entries (the constant-one variable) does not serialise on one thread:
-//   k_qap_segment_sum : one thread per segment (<= 256 entries of one row)  -> Jacobian partial sums
-//   k_qap_row_sum     : one thread per row over its segments                -> Jacobian row sums
+//   k_qap_segment_sum : one thread per segment (<= 256 entries of one row)      -> Jacobian partial sums
+//   k_qap_row_sum     : one thread per group of <= 256 partial sums of a row    -> second-level partial sums
+//   k_qap_row_sum     : one thread per row over its second-level sums           -> Jacobian row sums
 // followed by the usual batch normalisation + serialisation (k_normalize_encode).
 #pragma once
 #include "fft.cuh"

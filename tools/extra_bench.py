@@ -164,7 +164,51 @@ def pairing_latency(curve):
                       "thirty_two_checks_ms": round(t32 * 1e3, 2), "kernels_ms": prof}), flush=True)
 
 
+def qap(log2m):
+    """dot_product_vec over a synthetic R1CS-shaped matrix: 2^log2m constraints and variables, 1-4 entries per
+    variable (90 % +-1, 10 % general coefficients) plus the constant-one variable that touches every constraint."""
+    import random
+    from snark_setup_b200 import ffi as F
+    cv, cid, g = R.BLS12_377, S.BLS12_377, R.BLS12_377.g1
+    m = 1 << log2m
+    rng = random.Random(11)
+    gen = g.encode(g.gen, False) * m
+    bases = S.apply_powers(cid, S.G1, gen, False, S.CHECK_NO, False, m, tau=scalar(b"qap-tau", cv.r), first_power=0)
+    rows = [[(1, i) for i in range(m)]]
+    for _ in range(m - 1):
+        row = []
+        for _ in range(rng.randrange(1, 5)):
+            u = rng.random()
+            c = 1 if u < 0.6 else cv.r - 1 if u < 0.9 else rng.randrange(cv.r)
+            row.append((c, rng.randrange(m)))
+        rows.append(row)
+    nnz = sum(len(r) for r in rows)
+    S.qap_dot_product(cid, S.G1, bases, False, rows[:1024], True)  # warm-up
+    t0 = time.perf_counter()
+    out = S.qap_dot_product(cid, S.G1, bases, False, rows, True)
+    t = time.perf_counter() - t0
+    F.profile_enable(True)
+    F.profile_reset()
+    t1 = time.perf_counter()
+    S.qap_dot_product(cid, S.G1, bases, False, rows, True)
+    t_prof = time.perf_counter() - t1
+    prof = {k: round(v["ms"], 3) for k, v in sorted(F.profile_read().items())}
+    F.profile_enable(False)
+    ok = True
+    for v in (1, m // 2, m - 1):
+        idx = [i for _, i in rows[v]]
+        pts = b"".join(bases[i * 96:(i + 1) * 96] for i in idx)
+        want = O.msm(0, 0, pts, False, len(idx), [c for c, _ in rows[v]])
+        ok = ok and S.transcode(cid, S.G1, want, False, S.CHECK_NO, True) == out[v * 48:(v + 1) * 48]
+    print(json.dumps({"bench": "qap dot_product_vec (BLS12-377 G1)", "constraints": m, "variables": len(rows), "nnz": nnz,
+                      "seconds_incl_python_marshalling": round(t, 3), "kernels_ms": prof, "device_ms": round(sum(prof.values()), 1),
+                      "spot_check_vs_oracle_msm": ok, "path": "host buffers through ss_qap_dot_product"}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "qap":
+        qap(int(sys.argv[2]) if len(sys.argv) > 2 else 20)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pairing":
         pairing_latency("bls12_377")
         pairing_latency("bw6_761")
