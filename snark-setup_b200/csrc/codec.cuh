@@ -109,8 +109,8 @@ SS_HD bool in_subgroup_rmul(const Affine<typename G::F>& p) {
 // (g1.rs / g2.rs).  u = 0x8508c00000000001 has 7 set bits: 63+6 group operations per [u] instead of
 // 253+87, identical for every lane.  tests/test_oracle_cpu.py checks verdict equality with the
 // r-multiplication on subgroup points, random curve points, pure cofactor torsion and mixed points.
-// BW6-761 keeps the r-multiplication (ark-bw6-761 0.4.0 has no fast test).  -DSS_SUBGROUP_RMUL forces
-// the reference algorithm everywhere.
+// BW6-761 G1 has its own endomorphism test below; BW6-761 G2 keeps the r-multiplication.
+// -DSS_SUBGROUP_RMUL forces the reference algorithm everywhere.
 constexpr unsigned long long kBls377U = 0x8508c00000000001ull;
 
 template <class F>
@@ -162,6 +162,31 @@ SS_HD bool in_subgroup_endo(const Affine<Fp2<Bls377Fq>>& p, Bls377G2*) {
     F x = p.x, y = p.y;
     Endo<Bls377G2>::apply(1, x, y);  // psi(P)
     return jac_eq_affine(up, x, y);
+}
+// ---- endomorphism subgroup test for BW6-761 G1 --------------------------------------------------------
+// phi(x, y) = (beta x, y) acts on G1 as lambda with lambda^2 + lambda + 1 = 0 (mod r), and
+//     (u + 1) + (u^3 - u^2 + 1) * lambda = 0 (mod r)        (u = the BLS12-377 seed, checked in tests),
+// so psi = (u + 1) + (u^3 - u^2 + 1) phi kills G1.  Its norm a^2 - ab + b^2 is 3r: psi = (1 - phi) psi' up to a
+// unit of Z[phi], with ker psi' = G1 (order r) and ker(1 - phi) = {O, (0, +-sqrt(-1))}.  q = 3 (mod 4), so those
+// two points are not rational on y^2 = x^3 - 1 and, phi being defined over Fq, psi(P) = O for P in E(Fq) forces
+// psi'(P) = O: the test accepts EXACTLY G1 — the same predicate as the reference's r-multiplication
+// (elements.rs:138-142) at 252 doublings + 28 additions instead of 376 + 134.  (gnark-crypto's bw6-761 G1 uses
+// the same short vector.)  G2 keeps the r-multiplication: on y^2 = x^3 + 4 the point (0, 2) has order 3, is fixed
+// by phi and IS killed by psi, so the analogous test would accept G2 + <(0, 2)>.
+SS_HD bool in_subgroup_endo(const Affine<Fp<Bw6Fq>>& p, Bw6G1*) {
+    using F = Fp<Bw6Fq>;
+    if (p.inf) return true;
+    F beta;
+#pragma unroll
+    for (int i = 0; i < 24; i++) beta.l[i] = Bw6G1Glv::beta(i);
+    Affine<F> phip{fp_mul(p.x, beta), p.y, false};
+    Jac<F> t = jac_mul_u<F>(phip);              // u phi(P)
+    t = jac_madd(t, affine_neg(phip));          // (u - 1) phi(P)
+    t = jac_mul_u<F>(t);                        // (u^2 - u) phi(P)
+    t = jac_mul_u<F>(t);                        // (u^3 - u^2) phi(P)
+    t = jac_madd(t, phip);                      // (u^3 - u^2 + 1) phi(P)
+    Jac<F> s = jac_madd(jac_mul_u<F>(p), p);    // (u + 1) P
+    return jac_add(t, s).is_identity();
 }
 template <class G>
 SS_HD bool in_subgroup_endo(const Affine<typename G::F>& p, G*) {

@@ -111,6 +111,35 @@ def test_subgroup_test_equals_r_multiplication(L, gid):
         pts += [Pn, g.mul(Pn, g.r), g.add(g.mul(g.gen, rng.randrange(1, g.r)), g.mul(Pn, g.r))]
     if gid == 0:
         pts += [(q - 1, 0), (0, 1), (0, q - 1)]
+    if gid == 2:
+        # BW6-761 G1 (y^2 = x^3 - 1): the three points of order 2, small-order torsion obtained by clearing most of
+        # the group order from random points, subgroup points shifted by such torsion, and the relation the test
+        # rests on: (u + 1) + (u^3 - u^2 + 1) lambda = 0 (mod r), norm 3r, q = 3 (mod 4)
+        p6 = g.F.p
+        w = next(pow(c, (p6 - 1) // 3, p6) for c in range(2, 50) if pow(c, (p6 - 1) // 3, p6) != 1)
+        pts += [(1, 0), (w, 0), (w * w % p6, 0)]
+        a, b = U + 1, U ** 3 - U ** 2 + 1
+        assert a * a - a * b + b * b == 3 * g.r and p6 % 4 == 3
+        # group order by Cornacchia (q = x^2 + 3y^2; the six twists have traces +-2x, +-(x +- 3y)), confirmed on a
+        # random curve point; cofactor = 2^2 * 127 * (375-bit rest): points of order 2, 4, 127 and of "rest" order
+        from math import isqrt
+        aa, bb = p6, g.F.sqrt((-3) % p6)
+        while bb > isqrt(p6):
+            aa, bb = bb, aa % bb
+        x0, y0 = bb, isqrt((p6 - bb * bb) // 3)
+        assert x0 * x0 + 3 * y0 * y0 == p6
+        Pr = rnd()
+        orders = [p6 + 1 - t for t in (2 * x0, -2 * x0, x0 + 3 * y0, -x0 - 3 * y0, x0 - 3 * y0, 3 * y0 - x0)]
+        n = next(o for o in orders if o % g.r == 0 and g.mul(Pr, o) is None)
+        h = n // g.r
+        assert h % (4 * 127) == 0
+        rest = h // (4 * 127)
+        for cof in (n // 2, n // 4, n // 127, n // (2 * 127), n // rest, g.r * 4 * 127):
+            for _ in range(2):
+                Q = g.mul(rnd(), cof)
+                if Q is not None:
+                    assert not g.in_subgroup(Q)
+                    pts += [Q, g.add(Q, g.mul(g.gen, rng.randrange(1, g.r)))]
     for P in pts:
         rc = L.emul_in_subgroup(gid, g.encode(P, 0))
         assert rc == (3 if g.in_subgroup(P) else 0), (g.name, P, rc)
