@@ -56,7 +56,19 @@ def bw6(power):
     t_v = best(lambda: pairs.append(S.phase1_verification_vectors(sp, bytes(resp), True, newc, False, seed=seed)))
     tau = k0[0] * k1[0] % cv.r
     vok = all(O.apply_powers(1, g, s, False, 3, False, 1, powers=[tau]) == sx for (s, sx), g in zip(pairs[-1], (0, 1, 0, 0)))
+    from snark_setup_b200 import ffi as F
+    F.set_concurrent_vectors(False)  # serialised, so the event brackets see one kernel at a time
+    F.profile_enable(True)
+    F.profile_reset()
+    S.phase1_computation(sp, chal, resp, False, True, S.CHECK_NO, *k1)
+    prof_c = {k: round(v["ms"], 2) for k, v in sorted(F.profile_read().items())}
+    F.profile_reset()
+    S.phase1_verification_vectors(sp, bytes(resp), True, newc, False, seed=seed)
+    prof_v = {k: round(v["ms"], 2) for k, v in sorted(F.profile_read().items())}
+    F.profile_enable(False)
+    F.set_concurrent_vectors(True)
     print(json.dumps({"bench": "bw6_761 phase1", "power": power, "contribute_powers_per_s": N / t_c, "contribute_ms": t_c * 1e3,
+                      "contribute_kernels_ms_serialised": prof_c, "verify_kernels_ms_serialised": prof_v,
                       "verify_powers_per_s": N / t_v, "verify_ms": t_v * 1e3, "parity_spot_check": ok, "ratio_check": vok,
                       "path": "host buffers through ss_phase1_computation / ss_phase1_verification_vectors"}), flush=True)
 
