@@ -385,7 +385,8 @@ def main():
         roofline = {"bound": "int32-imad", "kernel": name, "achieved": ach, "peak": mac_peak, "unit": "TMAC32/s",
                     "frac": ach / mac_peak, "peak_source": "measured IMAD microbenchmark on this pool (profiles/imad_peak.json)"
                     if imad else "fallback 18.4 T IMAD/s / 2",
-                    "traffic": (imad or {}).get("scalar_mul_g1_dram_bytes_per_launch"),
+                    "traffic": (int((imad or {}).get("scalar_mul_g1_dram_bytes_per_element") * d["elements"] / max(1, d["launches"]))
+                                if (imad or {}).get("scalar_mul_g1_dram_bytes_per_element") and ".g1" in name else None),
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]), "kernel_share_of_step": d["ms"] / total_ms,
                     "whole_step_frac": W_REF_POWER * (value / world) * 1e-12 / mac_peak,
                     "executed": {"what": "MAC32 the kernel really executes (GLV/GLS algorithm, counted on the emulated "
