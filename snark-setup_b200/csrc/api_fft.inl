@@ -25,6 +25,18 @@ int log2_exact(uint64_t n) {
     return l;
 }
 
+// device scratch one fft_vector call carves from its lane
+size_t fft_scratch_bytes(const GroupOps& o, int log_n, uint64_t h_count, int in_c, int out_c) {
+    const uint64_t n = 1ull << log_n, nd = n + h_count, half = n >> 1;
+    const size_t isz = in_c ? o.csize : o.usize, osz = out_c ? o.csize : o.usize;
+    const size_t cw = (size_t)o.coord_words * 4, frw = o.fr_words;
+    const size_t io_b = std::max(isz * nd, osz * n);
+    const size_t seq_b = (size_t)(log_n + 64) * frw * 4;
+    return 256 + align_up(io_b, 256) + align_up(2 * cw * nd, 256) + align_up(nd, 256) + align_up(2 * cw * n, 256) +
+           align_up(n, 256) + align_up(3 * cw * std::max<uint64_t>(half, 2), 256) + align_up(3 * cw * n, 256) +
+           align_up(cw * n, 256) + align_up(seq_b, 256) + 256;
+}
+
 // One vector: decode n + h_count elements (n = 2^log_n), optionally emit the H query
 // h_i = P_(i+n) - P_i for i < h_count, then the n Lagrange coefficients.  in/out/h_out are HOST buffers.
 int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int log_n, uint64_t h_count, uint8_t* out,
@@ -46,9 +58,7 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
     const size_t cw = (size_t)o.coord_words * 4, frw = o.fr_words;
     const size_t io_b = std::max(isz * nd, osz * n);  // staged input, later reused for the serialized output
     const size_t seq_b = (size_t)(log_n + 64) * frw * 4;
-    const size_t need = 256 + align_up(io_b, 256) + align_up(2 * cw * nd, 256) + align_up(nd, 256) +
-                        align_up(2 * cw * n, 256) + align_up(n, 256) + align_up(3 * cw * std::max<uint64_t>(half, 2), 256) +
-                        align_up(3 * cw * n, 256) + align_up(cw * n, 256) + align_up(seq_b, 256) + 256;
+    const size_t need = fft_scratch_bytes(o, log_n, h_count, in_c, out_c);
     size_t free_b = 0, total_b = 0;
     CU(cudaSetDevice(device));
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -290,7 +300,21 @@ int ss_groth16_params_new(const ss_phase1_params* p, const uint8_t* accumulator,
                             jobs[v].h_out, compressed_output, jobs[v].what, v);
         if (rcs[v]) errs[v] = g_err;
     };
-    if (concurrent_vectors()) {
+    // concurrent lanes need all four scratch slabs at once: fall back to one transform at a time when the
+    // device holding the most of them could not fit its share
+    bool concurrent = concurrent_vectors();
+    if (concurrent) {
+        const size_t D = g_devices.size();
+        std::vector<size_t> per_dev(D, 0);
+        for (int v = 0; v < 4; v++)
+            per_dev[(size_t)v % D] += fft_scratch_bytes(*group_ops(p->curve, jobs[v].group), lm, jobs[v].h, compressed_input, compressed_output);
+        for (size_t d = 0; d < D && concurrent; d++) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaSetDevice(g_devices[d]) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) concurrent = false;
+            else if (per_dev[d] > total_b / 10 * 8) concurrent = false;
+        }
+    }
+    if (concurrent) {
         std::vector<std::thread> th;
         for (int v = 0; v < 4; v++) th.emplace_back(run, v);
         for (auto& t : th) t.join();
