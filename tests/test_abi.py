@@ -52,12 +52,43 @@ def test_argument_errors_are_reported_without_device():
         S.Phase1Parameters(7, 10, 256)
 
 
+def test_prepare_phase2_and_qap_host_logic_without_device():
+    """Sizes and argument validation of the SURVEY §8(f) entry points are host arithmetic (no compute call)."""
+    # groth16_utils.rs:65-69,134-168: domain = next power of two; bytes of Groth16Params::write
+    for cid, (u1, u2, c1, c2) in ((S.BLS12_377, (96, 192, 48, 96)), (S.BW6_761, (192, 192, 96, 96))):
+        for size, m in ((1, 1), (2, 2), (3, 4), (1000, 1024), (1 << 20, 1 << 20), ((1 << 20) + 1, 1 << 21)):
+            assert S.groth16_params_size(cid, size, False) == (m, 2 * u1 + u2 + 3 * m * u1 + m * u2 + (m - 1) * u1)
+            assert S.groth16_params_size(cid, size, True) == (m, 2 * c1 + c2 + 3 * m * c1 + m * c2 + (m - 1) * c1)
+    with pytest.raises(S.SetupError):          # 3 is not a radix-2 domain
+        S.group_ifft(S.BLS12_377, S.G1, bytes(96 * 3), False, False)
+    with pytest.raises(S.InvalidLength) as ei:  # h_query needs 2*degree - 1 powers (index panic in the reference)
+        S.h_query_groth16(S.BLS12_377, bytes(96 * 6), False, 4, False)
+    assert (ei.value.expected, ei.value.got) == (7, 6)
+    sp = S.Phase1Parameters(S.BLS12_377, 3, 8)
+    with pytest.raises(S.InvalidLength):        # domain 16 > 8 powers (groth16_utils.rs large_phase2_fails)
+        S.groth16_params_new(sp, bytes(sp.get_length(False)), False, 9, False)
+    with pytest.raises(S.InvalidLength):        # accumulator buffer too short
+        S.groth16_params_new(sp, bytes(100), False, 8, False)
+    bases = bytes(96 * 4)
+    with pytest.raises(S.InvalidLength):        # coeffs[ind] out of range
+        S.qap_dot_product(S.BLS12_377, S.G1, bases, False, [[(1, 4)]], False)
+    with pytest.raises(S.InvalidData):          # scalar >= r
+        S.qap_dot_product(S.BLS12_377, S.G1, bases, False, [[(R.BLS12_377.r, 0)]], False)
+
+
 @pytest.mark.skipif(_have_gpu(), reason="box has a GPU")
 def test_no_cpu_fallback():
     with pytest.raises(S.DeviceError):
         S.generate_powers_of_tau(S.BLS12_377, 5, 0, 4)
     with pytest.raises(S.DeviceError):
         S.apply_powers(S.BLS12_377, S.G1, bytes(96), False, S.CHECK_NO, True, 1, tau=3)
+    g1, g2 = R.BLS12_377.g1, R.BLS12_377.g2
+    with pytest.raises(S.DeviceError):
+        S.group_ifft(S.BLS12_377, S.G1, g1.encode(g1.gen, False) * 4, False, False)
+    with pytest.raises(S.DeviceError):
+        S.same_ratio(S.BLS12_377, g1.encode(g1.gen, False) * 2, g2.encode(g2.gen, False) * 2)
+    with pytest.raises(S.DeviceError):
+        S.qap_dot_product(S.BLS12_377, S.G1, g1.encode(g1.gen, False) * 2, False, [[(1, 0)]], False)
 
 
 def test_iter_chunk_matches_reference_schedule():
