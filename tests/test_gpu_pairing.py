@@ -154,3 +154,28 @@ def test_phase1_verification_ratios_verdicts(curve, power):
     bad[o + 4 * c1:o + 5 * c1] = cv.g1.encode(None, True)
     with pytest.raises(S.PointAtInfinity):
         S.phase1_verification_ratios(sp, bytes(bad), True, None, False, seed=seed)
+
+
+def test_phase2_contribute_then_verify_with_verdict():
+    """BASELINE config C5 in miniature (phase2/src/parameters.rs:286-307,393-407): contribute = delta^-1 batch_mul of
+    the H and L queries, verify = merge_pairs(before, after) fed to check_same_ratio against
+    (delta_after * G2, delta_before * G2) — all on the device; a tampered query element flips the verdict."""
+    cv, cid = R.BLS12_377, S.BLS12_377
+    g1, g2 = cv.g1, cv.g2
+    n = 1 << 12
+    rng = random.Random(2024)
+    tau, delta = rng.randrange(2, cv.r), rng.randrange(2, cv.r)
+    gens = g1.encode(g1.gen, False) * n
+    seed = hashlib.blake2b(b"phase2", digest_size=32).digest()
+    g2_pair = g2.write_batch([g2.mul(g2.gen, delta), g2.gen], False)   # (after.delta_g2, before.delta_g2)
+    for label, first in ((b"h", 1), (b"l", 7)):
+        before = S.apply_powers(cid, S.G1, gens, False, S.CHECK_NO, False, n, tau=tau, first_power=first)
+        after = bytearray(before)
+        S.batch_mul(cid, S.G1, after, pow(delta, -1, cv.r))
+        s, sx = S.merge_pairs(cid, S.G1, before, bytes(after), False, seed=seed)
+        S.check_same_ratio(cid, s + sx, g2_pair)
+        bad = bytearray(after)
+        bad[96 * 100:96 * 101] = after[96 * 101:96 * 102]
+        s, sx = S.merge_pairs(cid, S.G1, before, bytes(bad), False, seed=seed)
+        with pytest.raises(S.InvalidRatio):
+            S.check_same_ratio(cid, s + sx, g2_pair)
