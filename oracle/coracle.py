@@ -20,6 +20,8 @@ def lib():
         L.oracle_transcode.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t,
                                        C.c_int, C.POINTER(C.c_uint64)]
         L.oracle_msm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_group_ifft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_size_t,
+                                        C.POINTER(C.c_uint64)]
         L.oracle_powers.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.oracle_phase1_computation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64,
                                                 C.c_uint64, C.c_uint64, C.c_char_p, C.c_char_p, C.c_char_p]
@@ -82,6 +84,19 @@ def msm(curve, group, pts, compressed, n, scalars):
     if rc:
         raise OracleError(rc, 0)
     return out.raw
+
+
+def group_ifft(curve, group, inp, in_c, out_c, check=3):
+    """to_coeffs (setup-utils/src/groth16_utils.rs:44-53) by the C++ restatement (iterative decimation in frequency)."""
+    isz = SIZES[(curve, group)][1 if in_c else 0]
+    osz = SIZES[(curve, group)][1 if out_c else 0]
+    n = len(inp) // isz
+    out = C.create_string_buffer(max(1, n * osz))
+    bad = C.c_uint64(0)
+    rc = lib().oracle_group_ifft(curve, group, bytes(inp), int(in_c), check, out, int(out_c), n, C.byref(bad))
+    if rc:
+        raise OracleError(rc, bad.value)
+    return out.raw[:n * osz]
 
 
 def powers(curve, tau, start, end):

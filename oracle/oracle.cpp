@@ -110,6 +110,8 @@ struct Fp {
         return r;
     }
     Fp sqr() const { return *this * *this; }
+    static constexpr int TWO_ADICITY_ = P::TWO_ADICITY;
+    static Fp fft_root() { Fp r; memcpy(r.v, P::FFT_ROOT, sizeof r.v); return r; }  // ark-ff TWO_ADIC_ROOT_OF_UNITY
     static Fp from_raw(const uint64_t* raw) { Fp a, r2; memcpy(a.v, raw, sizeof a.v); memcpy(r2.v, P::R2, sizeof r2.v); return a * r2; }
     void to_raw(uint64_t* out) const { Fp o = zero(); o.v[0] = 1; Fp c = *this * o; memcpy(out, c.v, sizeof c.v); }
     Fp pow(const uint64_t* e, int n) const {
@@ -263,6 +265,17 @@ template <class F> Jac<F> jmul(const Aff<F>& b, const uint64_t* k, int nlimbs) {
     return acc;
 }
 
+// k * P for a Jacobian base (MSB-first double-and-add, the generic `Group *= scalar` of ark-ec)
+template <class F> Jac<F> jmul_jac(const Jac<F>& b, const uint64_t* k, int nlimbs) {
+    Jac<F> acc = Jac<F>::identity();
+    for (int i = nlimbs - 1; i >= 0; i--)
+        for (int bit = 63; bit >= 0; bit--) {
+            acc = jdbl(acc);
+            if ((k[i] >> bit) & 1) acc = jadd(acc, b);
+        }
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 struct BlsG1 {
     typedef Fp<OBls377Fq> F; typedef Fp<OBls377Fr> Fr;
@@ -400,6 +413,62 @@ int apply_powers(const uint8_t* in, int in_c, int check, uint8_t* out, int out_c
     return E_OK;
 }
 
+// to_coeffs (setup-utils/src/groth16_utils.rs:44-53): domain.ifft over the group + normalize_batch, restated as an
+// iterative decimation-in-frequency transform (Gentleman-Sande: butterflies (a, b) -> (a + b, w^j (a - b)), output in
+// bit-reversed order) followed by the 1/n scaling — every twiddle and the scaling a full double-and-add scalar
+// multiplication, as ark-poly's generic FFT over C::Group does (n/2 log n + n of them).
+template <class G>
+int group_ifft(const uint8_t* in, int in_c, int check, uint8_t* out, int out_c, size_t n, uint64_t* err_index) {
+    typedef typename G::F F; typedef typename G::Fr Fr;
+    const int isz = in_c ? G::CSIZE : G::USIZE, osz = out_c ? G::CSIZE : G::USIZE;
+    int log_n = 0;
+    while (((size_t)1 << log_n) < n) log_n++;
+    if (((size_t)1 << log_n) != n || log_n > Fr::TWO_ADICITY_) return E_INVALID_LENGTH;
+    std::vector<Jac<F>> v(n);
+    for (size_t i = 0; i < n; i++) {
+        Aff<F> p;
+        int e = decode<G>(in + i * isz, in_c != 0, check, p);
+        if (e) { if (err_index) *err_index = i; return e; }
+        v[i] = p.inf ? Jac<F>::identity() : Jac<F>{p.x, p.y, F::one()};
+    }
+    // F::get_root_of_unity: TWO_ADIC_ROOT_OF_UNITY squared down to order n; the inverse transform uses w^-1
+    Fr w = Fr::fft_root();
+    for (int i = log_n; i < Fr::TWO_ADICITY_; i++) w = w.sqr();
+    Fr winv = w.inv();
+    for (size_t half = n >> 1; half >= 1; half >>= 1) {
+        // twiddles of this stage: wm^j, wm = winv^(n / (2 half))
+        Fr wm = winv;
+        for (size_t s = n / (2 * half); s > 1; s >>= 1) wm = wm.sqr();
+        std::vector<Fr> tw(half);
+        tw[0] = Fr::one();
+        for (size_t j = 1; j < half; j++) tw[j] = tw[j - 1] * wm;
+#pragma omp parallel for schedule(dynamic, 16)
+        for (size_t t = 0; t < n / 2; t++) {
+            const size_t blk = t / half, j = t % half, lo = blk * 2 * half + j, hi = lo + half;
+            Jac<F> a = v[lo], b = v[hi];
+            v[lo] = jadd(a, b);
+            Jac<F> nb = b; nb.Y = nb.Y.neg();
+            Jac<F> d = jadd(a, nb);
+            uint64_t k[G::FRL]; tw[j].to_raw(k);
+            v[hi] = jmul_jac(d, k, G::FRL);
+        }
+    }
+    Fr nn = Fr::zero();
+    { uint64_t raw[G::FRL] = {0}; raw[0] = (uint64_t)n; nn = Fr::from_raw(raw); }
+    uint64_t kinv[G::FRL]; nn.inv().to_raw(kinv);
+    std::vector<Jac<F>> res(n);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < n; i++) {
+        size_t r = 0;
+        for (int b = 0; b < log_n; b++) r |= ((i >> b) & 1) << (log_n - 1 - b);
+        res[r] = jmul_jac(v[i], kinv, G::FRL);
+    }
+    std::vector<Aff<F>> aff;
+    normalize_batch(res, aff);
+    for (size_t i = 0; i < n; i++) encode<G>(out + i * osz, out_c != 0, aff[i]);
+    return E_OK;
+}
+
 template <class G>
 int transcode(const uint8_t* in, int in_c, int check, uint8_t* out, int out_c, size_t n, int rmul, uint64_t* err_index) {
     typedef typename G::F F;
@@ -468,6 +537,14 @@ int oracle_transcode(int curve, int group, const uint8_t* in, int in_c, int chec
 #define CALL(G) transcode<G>(in, in_c, check, out, out_c, n, rmul_subgroup, err_index)
     DISPATCH(curve, group, CALL);
 #undef CALL
+}
+
+int oracle_group_ifft(int curve, int group, const uint8_t* in, int in_c, int check, uint8_t* out, int out_c, size_t n,
+                      uint64_t* err_index) {
+    if (curve == 0) return group == 0 ? group_ifft<BlsG1>(in, in_c, check, out, out_c, n, err_index)
+                                      : group_ifft<BlsG2>(in, in_c, check, out, out_c, n, err_index);
+    return group == 0 ? group_ifft<BwG1>(in, in_c, check, out, out_c, n, err_index)
+                      : group_ifft<BwG2>(in, in_c, check, out, out_c, n, err_index);
 }
 
 int oracle_msm(int curve, int group, const uint8_t* pts, int compressed, size_t n, const uint8_t* scalars, uint8_t* out) {

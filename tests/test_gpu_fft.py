@@ -97,6 +97,19 @@ def test_group_ifft_known_discrete_logs(curve, grp, log_n):
     assert S.group_ifft(cid, grp, pts, False, True) == want
 
 
+@pytest.mark.parametrize("curve,grp,log_n", [("bls12_377", 0, 11), ("bls12_377", 1, 9), ("bw6_761", 0, 8), ("bw6_761", 1, 8)])
+def test_group_ifft_matches_cpp_oracle(curve, grp, log_n):
+    """Random subgroup points (no structure), device vs oracle.cpp::group_ifft (iterative decimation in frequency)."""
+    cv = R.CURVES[curve]
+    g = _group(cv, grp)
+    cid = CID[curve]
+    n = 1 << log_n
+    gens = g.encode(g.gen, False) * n
+    pts = O.apply_powers(cid, grp, gens, False, 3, False, n, tau=0x1234567 + log_n, first_power=3, coeff=987654321)
+    for cout in (True, False):
+        assert S.group_ifft(cid, grp, pts, False, cout) == O.group_ifft(cid, grp, pts, False, cout)
+
+
 @pytest.mark.parametrize("curve", ["bls12_377", "bw6_761"])
 def test_h_query(curve):
     cv = R.CURVES[curve]

@@ -107,3 +107,28 @@ def test_known_discrete_logs_route(cid, cv):
     w = R.get_root_of_unity(cv.r, n)
     for k in (0, 1, n - 1):
         assert sum(c[j] * pow(w, j * k, cv.r) for j in range(n)) % cv.r == s[k]
+
+
+@pytest.mark.parametrize("cid,cv", CURVES, ids=["bls12_377", "bw6_761"])
+def test_cpp_oracle_group_ifft(cid, cv):
+    """oracle.cpp::group_ifft (iterative decimation in frequency, double-and-add twiddles — the reference algorithm's
+    cost profile) against the pyref algorithms and the golden Groth16Params coefficients."""
+    rng = random.Random(21 + cid)
+    for gid, g in ((0, cv.g1), (1, cv.g2)):
+        for n in (1, 2, 16 if cid == 0 else 4):
+            pts = [g.mul(g.gen, rng.randrange(1, cv.r)) for _ in range(n)]
+            if n > 2:
+                pts[1] = None
+            want = g.write_batch(R.group_ifft_fast(g, pts), True)
+            assert O.group_ifft(cid, gid, g.write_batch(pts, False), False, True) == want
+            assert O.group_ifft(cid, gid, g.write_batch(pts, True), True, True) == want
+    v = HOT["phase1"][cv.name]
+    p = R.Phase1Parameters(cv, v["power"], v["batch_size"])
+    acc = bytes.fromhex(v["challenge1"])
+    gold = bytes.fromhex(GOLD["curves"][cv.name]["params"]["4"]["compressed"])
+    s1c, s2c = cv.g1.size(True), cv.g2.size(True)
+    (o1, _, z1), (o2, _, z2) = p.split_offsets(False)[:2]
+    assert O.group_ifft(cid, 0, acc[o1:o1 + 4 * z1], False, True) == gold[2 * s1c + s2c:2 * s1c + s2c + 4 * s1c]
+    assert O.group_ifft(cid, 1, acc[o2:o2 + 4 * z2], False, True) == gold[2 * s1c + s2c + 4 * s1c:2 * s1c + s2c + 4 * s1c + 4 * s2c]
+    with pytest.raises(O.OracleError):
+        O.group_ifft(cid, 0, cv.g1.encode(cv.g1.gen, False) * 3, False, True)

@@ -130,26 +130,26 @@ def prepare_phase2(curve, power):
     o = rp.split_offsets(False)[0][0]
     ok = s_ == acc[o + s1:o + 2 * s1]
     smuls = 4 * ((power - 1) * m // 2 + 2)
-    # CPU port: the reference algorithm spends n/2*log n full scalar multiplications per vector (ark-poly's
-    # radix-2 FFT over C::Group) + n for the 1/n scaling; time a sample of them on the host cores
-    k = 1 << 12
-    gens = cv.g1.encode(cv.g1.gen, False) * k
+    # CPU port: oracle.cpp::group_ifft (reference algorithm: n/2*log n + n double-and-add scalar multiplications per
+    # vector, OpenMP over all host cores) timed on a 2^ks-element sample of the same vectors, scaled by the exact
+    # operation count ratio (the work per scalar multiplication does not depend on n)
+    ks = min(power, 10)
+    o1, o2 = rp.split_offsets(False)[0][0], rp.split_offsets(False)[1][0]
     t1 = time.perf_counter()
-    O.apply_powers(cid, 0, gens, False, 3, False, k, tau=keys[0], first_power=1)
-    t_g1 = (time.perf_counter() - t1) / k
-    gens2 = cv.g2.encode(cv.g2.gen, False) * k
+    O.group_ifft(cid, 0, acc[o1:o1 + (s1 << ks)], False, False)
+    t_g1 = time.perf_counter() - t1
     t1 = time.perf_counter()
-    O.apply_powers(cid, 1, gens2, False, 3, False, k, tau=keys[0], first_power=1)
-    t_g2 = (time.perf_counter() - t1) / k
-    per_vec = m * power // 2 + m
-    cpu_s = per_vec * (3 * t_g1 + t_g2)
+    O.group_ifft(cid, 1, acc[o2:o2 + (s2 << ks)], False, False)
+    t_g2 = time.perf_counter() - t1
+    scale = (m * power / 2 + m) / ((1 << ks) * ks / 2 + (1 << ks))
+    cpu_s = scale * (3 * t_g1 + t_g2)
     print(json.dumps({"bench": "prepare_phase2 (Groth16Params::new + write)", "curve": curve, "power": power,
                       "phase2_size": m, "seconds": round(t, 4), "coefficients_per_s": round(4 * m / t),
                       "scalar_muls": smuls, "output_bytes": len(out[0]), "forward_evaluation_check": ok,
                       "kernels_ms": prof,
                       "cpu_port_estimate_s": round(cpu_s, 1), "cpu_cores": O.threads(),
-                      "cpu_note": "C++ oracle scalar-mul rate on the host cores x the reference algorithm's "
-                                  "n/2*log n + n multiplications per vector (3 G1 + 1 G2)",
+                      "cpu_note": "oracle.cpp::group_ifft (reference algorithm) on a 2^%d-element sample of each vector on all "
+                                  "host cores, scaled by the n/2*log n + n operation count (3 G1 + 1 G2 transforms)" % ks,
                       "path": "host buffers through ss_groth16_params_new"}), flush=True)
 
 
