@@ -20,6 +20,7 @@
 //   merge_pairs/power_pairs  setup-utils/src/helpers.rs:371-390 (msm_bigint: Pippenger)
 //   apply_powers             phase1/src/helpers/buffers.rs:77-97
 //   Phase1::computation      phase1/src/computation.rs:40-193 (Groth16)
+//   to_coeffs                setup-utils/src/groth16_utils.rs:44-53 (group IFFT, double-and-add twiddles)
 // Arithmetic: Montgomery CIOS on 64-bit limbs with unsigned __int128 (ark-ff MontBackend uses the
 // same limb size), Jacobian a=0 formulas dbl-2009-l / madd-2007-bl as ark-ec 0.4 does.
 #include <omp.h>

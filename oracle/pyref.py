@@ -23,6 +23,9 @@ reference's call sites:
   * iter_chunk                  phase1/src/helpers/buffers.rs:22-73
   * Phase1Parameters sizes      phase1/src/objects/parameters.rs:115-294
   * Phase1::computation         phase1/src/computation.rs:16-193 (Groth16 branch)
+  * to_coeffs / h_query / Groth16Params::new + ::write   setup-utils/src/groth16_utils.rs:44-168
+  * same_ratio / check_same_ratio                         setup-utils/src/helpers.rs:406-424 (verdict only: Tate pairing)
+  * dot_product(_vec) / eval / process_matrix             phase2/src/polynomial.rs:11-94, parameters.rs:96-105
 """
 from __future__ import annotations
 
