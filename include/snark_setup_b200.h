@@ -184,6 +184,10 @@ typedef struct {
 
 int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out);
 
+/* Phase1::initialization — phase1/src/initialization.rs:12-57: the blank accumulator (every element = the group
+ * generator, BatchSerializer::init_element, setup-utils/src/io/write.rs:45-55).  The hash prefix is not written. */
+int ss_phase1_initialization(const ss_phase1_params* p, uint8_t* output, size_t output_len, int compressed_output);
+
 /* iter_chunk — phase1/src/helpers/buffers.rs:22-73: the window schedule (start, end) of the reference's
  * batch loop (windows overlap by one element).  starts/ends may be NULL to query *count only. */
 int ss_phase1_iter_chunk(const ss_phase1_params* p, uint64_t* starts, uint64_t* ends, size_t max_windows, size_t* count);

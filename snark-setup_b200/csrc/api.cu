@@ -983,6 +983,48 @@ int ss_phase1_decompress(const ss_phase1_params* p, const uint8_t* in, size_t in
 
 int ss_phase1_sizes_of(const ss_phase1_params* p, ss_phase1_sizes* out) { return phase1_sizes(p, out); }
 
+// Phase1::initialization — phase1/src/initialization.rs:12-57: every slot of the accumulator holds the group
+// generator (BatchSerializer::init_element, setup-utils/src/io/write.rs:45-55).  The generator is serialized once
+// on the device (encode_point) and replicated into the caller's buffer; the 64-byte hash prefix is not touched.
+int ss_phase1_initialization(const ss_phase1_params* p, uint8_t* output, size_t output_len, int compressed_output) {
+    if (!p || !output) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    ss_phase1_sizes z;
+    int rc = phase1_sizes(p, &z);
+    if (rc) return rc;
+    const GroupOps* gs[2] = {group_ops(p->curve, SS_G1), group_ops(p->curve, SS_G2)};
+    const uint64_t s1 = compressed_output ? gs[0]->csize : gs[0]->usize, s2 = compressed_output ? gs[1]->csize : gs[1]->usize;
+    uint64_t off[5];
+    vector_offsets(p->curve, z, compressed_output, off);
+    const bool has_beta_g2 = true;  // every chunk buffer carries a beta_g2 slot (parameters.rs get_length) and init_element fills it
+    const uint64_t need = off[4] + s2;
+    if (output_len < need) return fail(SS_ERR_INVALID_LENGTH, 0, need, output_len, "output buffer too short");
+    if ((rc = ensure_init())) return rc;
+    LaneGuard lg;
+    if ((rc = lane_acquire(g_devices[0], 1024, &lg.l))) return rc;
+    uint8_t gen[2][192];
+    for (int g = 0; g < 2; g++) {
+        gs[g]->generator(reinterpret_cast<uint32_t*>(lg.l->buf) + g * 64, compressed_output, lg.l->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(gen[g], lg.l->buf + g * 256, g ? s2 : s1, cudaMemcpyDeviceToHost, lg.l->stream));
+    }
+    CU(cudaStreamSynchronize(lg.l->stream));
+    auto fill = [&](uint8_t* dst, const uint8_t* el, uint64_t sz, uint64_t count) {
+        if (!count) return;
+        memcpy(dst, el, sz);
+        for (uint64_t done = 1; done < count;) {  // doubling copies
+            const uint64_t k = std::min(done, count - done);
+            memcpy(dst + done * sz, dst, k * sz);
+            done += k;
+        }
+    };
+    fill(output + off[0], gen[0], s1, z.g1_chunk_size);
+    fill(output + off[1], gen[1], s2, z.other_chunk_size);
+    fill(output + off[2], gen[0], s1, z.other_chunk_size);
+    fill(output + off[3], gen[0], s1, z.other_chunk_size);
+    if (has_beta_g2) fill(output + off[4], gen[1], s2, 1);
+    return SS_OK;
+}
+
 // iter_chunk — phase1/src/helpers/buffers.rs:22-73: the reference's window schedule (windows of
 // batch_size elements, consecutive windows overlapping by one).  Host index arithmetic only; the engine
 // itself tiles whole vectors, this is exported for callers that keep the reference's loop structure.

@@ -435,6 +435,13 @@ __global__ void k_sum_points(const uint32_t* pts, int count, uint32_t* out, unsi
     encode_point<G>(out, false, r);
 }
 
+// ---- init_element (setup-utils/src/io/write.rs:45-55): the serialized group generator --------------------------
+template <class G>
+__global__ void k_generator(uint32_t* out, int compressed) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    encode_point<G>(out, compressed != 0, G::generator());
+}
+
 // ---- function table seen by api.cu -------------------------------------------------------------
 struct GroupOps {
     const char* name;      // e.g. "bls12_377.g1" (profiling labels)
@@ -452,6 +459,7 @@ struct GroupOps {
     void (*encode)(const EncodeArgs&, cudaStream_t);
     void (*subgroup)(const SubgroupArgs&, cudaStream_t);
     void (*sum_points)(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status, cudaStream_t);
+    void (*generator)(uint32_t* out, int compressed, cudaStream_t);
 };
 
 template <class G>
@@ -492,6 +500,7 @@ struct GroupLaunch {
     static void sum_points(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status, cudaStream_t s) {
         k_sum_points<G><<<1, 32, 0, s>>>(pts, count, out, status);
     }
+    static void generator(uint32_t* out, int compressed, cudaStream_t s) { k_generator<G><<<1, 32, 0, s>>>(out, compressed); }
     static GroupOps ops() {
         GroupOps o;
         o.name = G::name();
@@ -509,6 +518,7 @@ struct GroupLaunch {
         o.encode = &encode;
         o.subgroup = &subgroup;
         o.sum_points = &sum_points;
+        o.generator = &generator;
         return o;
     }
 };

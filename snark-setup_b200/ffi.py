@@ -385,6 +385,16 @@ class Phase1Parameters:
         return [(a[i], b[i]) for i in range(cnt.value)]
 
 
+def phase1_initialization(params, compressed_output):
+    """Phase1::initialization (phase1/src/initialization.rs:12-57) -> the blank accumulator (hash prefix zero)."""
+    f = lib().ss_phase1_initialization
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int]
+    out = bytearray(params.get_length(compressed_output))
+    po, k1 = _buf(out)
+    _check(f(C.byref(params.c), po, len(out), int(compressed_output)))
+    return bytes(out)
+
+
 def phase1_aggregate_chunk(chunk_params, chunk, compressed_chunk, full: bytearray, compressed_full):
     """One iteration of Phase1::aggregation (phase1/src/aggregation.rs:11-180); `full` is written in place."""
     f = lib().ss_phase1_aggregate_chunk
