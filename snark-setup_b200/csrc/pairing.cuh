@@ -21,7 +21,7 @@
 //     over u (64 bits, Miller points on the twist over Fq2, lines at positions 1, w, w^3 — see miller_ate) instead of
 //     the Tate loop over r (253 bits), and the hard part is a 4-way simultaneous exponentiation over the base-q
 //     digits of the exponent (314 bits: f^(q^i) by the q-power Frobenius c_k -> conj(c_k) gamma^k).  BW6-761 keeps
-//     the plain forms.
+//     the Tate loop and shortens the hard part to a 2-way exponentiation f^a0 (f^q)^a1 (572 bits, FROB2).
 // O(1) work per verification (4 checks per response): latency, not throughput, is what matters here.
 #pragma once
 #include "codec.cuh"
@@ -58,6 +58,7 @@ struct Bls377Pairing {
     static constexpr bool XI_ON_CONST = false;
     static constexpr bool ATE = true;            // Miller loop over u on the twist (64 bits) instead of r on G1 (253)
     static constexpr bool FROB4 = true;          // hard part as a 4-way simultaneous exponentiation over f^(q^i)
+    static constexpr bool FROB2 = false;
     SS_D static F mul_xi(const F& a) { return F{fp_neg(fp_mul5(a.c1)), a.c0}; }  // xi = u, u^2 = -5
 };
 struct Bw6Pairing {
@@ -70,6 +71,7 @@ struct Bw6Pairing {
     static constexpr bool XI_ON_CONST = true;
     static constexpr bool ATE = false;
     static constexpr bool FROB4 = false;
+    static constexpr bool FROB2 = true;  // hard part as f^a0 * (f^q)^a1 with the Gauss-reduced (a0, a1), 572 bits
     SS_D static F mul_xi(const F& a) { return fp_neg(fp_dbl(fp_dbl(a))); }  // xi = -4
 };
 
@@ -312,6 +314,20 @@ __global__ void __launch_bounds__(32) k_same_ratio(const uint32_t* g1_pairs, con
             int m = 0;
 #pragma unroll
             for (int d = 0; d < 4; d++) m |= (int)((PP::hardq(d, i >> 5) >> (i & 31)) & 1) << d;
+            if (m) acc = ext_mul<C>(acc, tab[m], k);
+        }
+    } else if constexpr (C::FROB2) {
+        // a0 + a1 q = c * hard with gcd(c, r) = 1 (tools/gen_constants.py): f2^(a0 + a1 q) = 1 <=> f2^hard = 1, and
+        // f2^q costs one Frobenius (the multipliers zeta^k already loaded in z: for k = 6 the Q of the easy part is q)
+        F tab[4];
+        tab[1] = f2;
+        tab[2] = fscale(f2, z);
+        tab[3] = ext_mul<C>(tab[1], tab[2], k);
+        acc = k == 0 ? F::one() : F::zero();
+#pragma unroll 1
+        for (int i = PP::HARD2_BITS - 1; i >= 0; i--) {
+            acc = ext_mul<C>(acc, acc, k);
+            const int m = (int)((PP::hard2(0, i >> 5) >> (i & 31)) & 1) | ((int)((PP::hard2(1, i >> 5) >> (i & 31)) & 1) << 1);
             if (m) acc = ext_mul<C>(acc, tab[m], k);
         }
     } else {
