@@ -92,6 +92,20 @@ SS_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// a + b WITHOUT the conditional subtraction: the result is < 2p and may only feed fp_mul / fp_sqr, whose
+// Montgomery reduction tolerates operands below 2p (the product before the final subtraction is below
+// (4p^2 + R p)/R = p (1 + 4p/R) < 1.04 p for the moduli here, which leave >= 7 spare bits in R = 2^(32 N)).
+template <class P>
+SS_HD Fp<P> fp_add_nr(const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    Fp<P> r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);
+    return r;
+}
+
 template <class P>
 SS_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
     constexpr int N = P::N;

@@ -48,7 +48,11 @@ template <class P>
 SS_HD Fp2<P> fp_mul(const Fp2<P>& a, const Fp2<P>& b) {
     Fp<P> v0 = fp_mul(a.c0, b.c0);
     Fp<P> v1 = fp_mul(a.c1, b.c1);
+#if defined(SS_FP2_REDUCED_SUMS)
     Fp<P> s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+#else
+    Fp<P> s = fp_mul(fp_add_nr(a.c0, a.c1), fp_add_nr(b.c0, b.c1));  // operand sums stay below 2p (fp.cuh)
+#endif
     Fp2<P> r;
     r.c1 = fp_sub(fp_sub(s, v0), v1);
     r.c0 = fp_sub(v0, fp_mul5(v1));
@@ -60,7 +64,11 @@ SS_HD Fp2<P> fp_mul(const Fp2<P>& a, const Fp2<P>& b) {
 template <class P>
 SS_HD Fp2<P> fp_sqr(const Fp2<P>& a) {
     Fp<P> v = fp_mul(a.c0, a.c1);
+#if defined(SS_FP2_REDUCED_SUMS)
     Fp<P> t = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, fp_mul5(a.c1)));
+#else
+    Fp<P> t = fp_mul(fp_add_nr(a.c0, a.c1), fp_sub(a.c0, fp_mul5(a.c1)));
+#endif
     Fp<P> v2 = fp_dbl(v);
     Fp2<P> r;
     r.c0 = fp_add(t, fp_dbl(v2));
