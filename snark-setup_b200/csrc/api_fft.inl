@@ -137,19 +137,23 @@ int fft_vector(int curve, int group, const uint8_t* in, int in_c, int check, int
         normalize(jac_t, 2, nullptr);
         for (int st_i = 0; st_i < log_n; st_i++) {
             const uint32_t* tw = nullptr;
+            uint64_t tw_count = half;
             if (st_i > 0) {
-                a.n = half;
+                const uint64_t m = 1ull << st_i;
+                tw_count = half - half / m + 1;  // every j >= 1, plus (block 0, j 0) whose twiddle is n^-1
+                a.fft_compact = 1;
+                a.n = tw_count;
                 a.tau_tab = seq + (size_t)(log_n - 1 - st_i) * frw;  // table of w_s^(2^j), w_s = w^(-n/2m)
                 a.has_coeff = 1;
                 a.coeff_limit = 1ull << st_i;  // block 0
                 a.power_mask = (1ull << st_i) - 1;
                 a.src_log_m = st_i;
                 a.jac = jac_t;
-                ProfScope ps("k_scalar_mul", o.name, half, s);
+                ProfScope ps("k_scalar_mul", o.name, tw_count, s);
                 o.scalar_mul(a, s);
                 tw = jac_t;
             }
-            ButterflyArgs b = {aff, inf, tw, n, st_i, jac_o};
+            ButterflyArgs b = {aff, inf, tw, n, st_i, jac_o, tw_count, st_i > 0 ? 1 : 0};
             { ProfScope ps("k_fft_butterfly", o.name, half, s); f.butterfly(b, s); }
             normalize(jac_o, n, st_i == log_n - 1 ? io : nullptr);
         }

@@ -9,7 +9,8 @@
 // is bit-identical to arkworks' in_order_ifft_in_place.  Here: radix-2 decimation in time.
 //   1. bit-reversal gather of the decoded points                                  k_fft_bitrev   (HBM-bound)
 //   2. stage s = 0 .. log n - 1 (half-size m = 2^s, w_s = w^(-n/2m)):
-//        t_i  = w_s^(i mod m) * upper_i      k_scalar_mul on n/2 gathered elements (skipped for s = 0: w_0^0 = 1)
+//        t_i  = w_s^(i mod m) * upper_i      k_scalar_mul on the gathered upper elements whose twiddle is not 1
+//                                            (none for s = 0; j = 0 of every block but block 0 is skipped)
 //        lo', hi' = lo + t, lo - t           k_fft_butterfly, two mixed additions (exceptional cases handled)
 //        batch-normalise to affine           k_normalize_encode -> affine scratch (last stage: serialized bytes)
 //   The final scaling by n^-1 costs no scalar multiplications of its own: block 0 of every stage uses the
@@ -17,7 +18,7 @@
 //   elements 0 and 1 are multiplied by n^-1 directly before the twiddle-free stage 0.
 // Twiddle scalars are never materialised: thread i derives w_s^(i mod m) from the table of w_s^(2^j), which for
 // every stage is a window of ONE sequence seq[j] = (w^-1)^(2^j) (w_s^(2^j) = seq[log n - 1 - s + j]).
-// Work: (log n - 1) * n/2 + 2 scalar multiplications — the integer-multiply pipe bounds it like batch_exp.
+// Work: about (log n - 2) * n/2 scalar multiplications — the integer-multiply pipe bounds it like batch_exp.
 #pragma once
 #include "kernels.cuh"
 
@@ -78,10 +79,14 @@ SS_D void store_jac_soa(uint32_t* jac, uint64_t stride, uint64_t i, const Jac<ty
 struct ButterflyArgs {
     const uint32_t* aff;  // n affine points (stage input)
     const uint8_t* inf;
-    const uint32_t* tw;  // twiddled upper halves, Jacobian SoA [3*FW][n/2], or nullptr (twiddle 1: read aff)
+    const uint32_t* tw;  // twiddled upper halves, Jacobian SoA [3*FW][tw_count], or nullptr (twiddle 1: read aff)
     uint64_t n;          // power of two >= 2
     int log_m;           // stage: half-size m = 2^log_m
     uint32_t* jac;       // out: Jacobian SoA [3*FW][n], natural positions
+    // compact twiddle array (ScalarMulArgs::fft_compact): entry 0 = (block 0, j 0), entry 1 + blk (m-1) + (j-1) for
+    // j >= 1; the j = 0 butterflies of the other blocks have twiddle 1 and read their upper element from `aff`
+    uint64_t tw_count;
+    int compact;
 };
 
 // butterfly i: lo = ((i >> s) << (s+1)) | (i & (m-1)), hi = lo | m;  (lo, hi) <- (lo + t, lo - t)
@@ -95,8 +100,10 @@ __global__ void __launch_bounds__(128) k_fft_butterfly(ButterflyArgs a) {
     const uint64_t lo = ((i >> a.log_m) << (a.log_m + 1)) | (i & (m - 1)), hi = lo | m;
     Affine<F> u = load_affine<G>(a.aff, a.inf, a.n, lo);
     Jac<F> t;
-    if (a.tw) {
-        t = load_jac_soa<G>(a.tw, half, i);
+    const uint64_t blk = i >> a.log_m, j = i & (m - 1);
+    if (a.tw && !(a.compact && j == 0 && blk != 0)) {
+        const uint64_t ti = a.compact ? (j == 0 ? 0 : 1 + blk * (m - 1) + (j - 1)) : i;
+        t = load_jac_soa<G>(a.tw, a.tw_count, ti);
     } else {
         Affine<F> v = load_affine<G>(a.aff, a.inf, a.n, hi);
         t = v.inf ? Jac<F>::identity() : Jac<F>{v.x, v.y, F::one()};

@@ -257,6 +257,9 @@ struct ScalarMulArgs {
     int src_log_m = -1;
     uint64_t coeff_limit = ~0ull;
     const uint32_t* gather = nullptr;  // sparse dot products (qap.cuh): thread i multiplies aff[gather[i]]
+    // fft_compact: the stage skips the butterflies whose twiddle is 1 (j = 0 of every block but block 0, whose
+    // twiddle carries the 1/n): thread 0 is (block 0, j 0), thread t >= 1 is block (t-1)/(m-1), j = 1 + (t-1)%(m-1).
+    int fft_compact = 0;
 };
 
 // bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
@@ -272,10 +275,16 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
     constexpr int FRW = FrP::N;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    uint64_t src = i;
+    uint64_t src = i, pw = i & a.power_mask;
     if (a.src_log_m >= 0) {
         const uint64_t m = 1ull << a.src_log_m;
-        src = ((i >> a.src_log_m) << (a.src_log_m + 1)) | m | (i & (m - 1));
+        uint64_t blk = i >> a.src_log_m, j = i & (m - 1);
+        if (a.fft_compact) {
+            blk = i ? (i - 1) / (m - 1) : 0;
+            j = i ? 1 + (i - 1) % (m - 1) : 0;
+            pw = j;
+        }
+        src = (blk << (a.src_log_m + 1)) | m | j;
     } else if (a.gather) {
         src = a.gather[i];
     }
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
             s = fp_mul(s, c);  // canonical * Montgomery -> canonical
         }
     } else {
-        s = tau_power<FrP>(a.tau_tab, a.first_power + (i & a.power_mask));
+        s = tau_power<FrP>(a.tau_tab, a.first_power + pw);
         if (a.has_coeff && i < a.coeff_limit) {
             Fp<FrP> c;
 #pragma unroll
