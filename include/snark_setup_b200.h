@@ -99,6 +99,14 @@ int ss_profile_read(ss_profile_entry* out, int max_entries);
  * (phase1/src/computation.rs:68-188).  Results are identical either way. */
 void ss_set_concurrent_vectors(int on);
 
+/* Scalar multiplication of bases that were read WITHOUT a subgroup check (CheckForCorrectness::No / OnlyNonZero —
+ * the reference's contribute default, setup-utils/src/helpers.rs:550).  Default (0): the GLV / GLS path, whose
+ * result equals the reference's `mul_bigint` for every point of the order-r subgroup — which is what a ceremony's
+ * challenge holds, the coordinator having verified it.  1: such bases go through the reference's own MSB-first
+ * double-and-add, which reproduces `mul_bigint` on ANY input (off-subgroup, even off-curve) at ~2x the cost.
+ * Inputs read with Full / OnlyInGroup always take the fast path. */
+void ss_set_strict_unchecked_inputs(int on);
+
 /* buffer_size::<C>(compression) — setup-utils/src/io/mod.rs:13-15 */
 size_t ss_element_size(int curve, int group, int compressed);
 size_t ss_scalar_size(int curve);
@@ -169,7 +177,7 @@ int ss_apply_powers(int curve, int group, const uint8_t* in, int in_compressed, 
 /* Phase1Parameters — phase1/src/objects/parameters.rs:115-294 */
 typedef struct {
     int curve;             /* ss_curve */
-    int proving_system;    /* ss_proving_system (only SS_GROTH16 is accelerated in this round) */
+    int proving_system;    /* ss_proving_system */
     int contribution_mode; /* ss_contribution_mode */
     uint64_t chunk_index;
     uint64_t chunk_size;
@@ -205,6 +213,22 @@ int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, si
                               size_t output_len, int compressed_input, int compressed_output, int check_input,
                               const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, void* stream);
 
+/* Index-range shards of ONE ceremony (the chunk ranges of phase1/src/objects/parameters.rs:248-294 cut
+ * finer): every vector of the buffer described by `p` is divided into `shard_count` equal contiguous parts and the
+ * call processes part `shard_index`; element i of a vector still receives tau^(first + i).  `input` / `output` are
+ * the WHOLE challenge / response buffers (typically the same files mapped by one process per GPU) and only the
+ * shard's byte ranges are read and written — the contract the reference's sibling rayon tasks already rely on
+ * (computation.rs:82-186).  beta_g2 belongs to shard 0.  No inter-process traffic.  With several devices selected in
+ * ss_init the shard is divided once more among them. */
+int ss_phase1_computation_shard(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
+                                size_t output_len, int compressed_input, int compressed_output, int check_input,
+                                const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t shard_index,
+                                uint32_t shard_count);
+int ss_phase1_computation_shard_dev(const ss_phase1_params* p, const void* d_input, size_t input_len, void* d_output,
+                                    size_t output_len, int compressed_input, int compressed_output, int check_input,
+                                    const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t shard_index,
+                                    uint32_t shard_count, void* stream);
+
 /* The per-vector hot loop of Phase1::verification — phase1/src/verification.rs:217-411 (Groth16) —
  * over a whole response: for tau_g1, tau_g2, alpha_g1, beta_g1: nonzero + subgroup check, the
  * power_pairs (s, sx) for the caller's check_same_ratio, and the vector re-encoded into
@@ -239,6 +263,26 @@ int ss_phase1_verification_vectors_dev(const ss_phase1_params* p, const void* d_
                                        int compressed_output, void* d_new_challenge, size_t new_challenge_len,
                                        int compressed_new_challenge, int subgroup_mode, int ratio_check,
                                        const uint8_t* rho_seed, uint8_t* pairs, void* stream);
+
+/* Shard `shard_index` of `shard_count` of the verification loop (see ss_phase1_computation_shard).  The shard reads
+ * ONE element beyond its range where its last ratio pair continues into the next shard (power_pairs pairs v[i] with
+ * v[i+1], setup-utils/src/helpers.rs:388-390 — the reason iter_chunk overlaps its windows, buffers.rs:54); rho_i is
+ * keyed by the global element index.  `pairs` receives the shard's PARTIAL sums (an empty shard: identities). */
+int ss_phase1_verification_vectors_shard(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
+                                         int compressed_output, uint8_t* new_challenge, size_t new_challenge_len,
+                                         int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                         const uint8_t* rho_seed, uint8_t* pairs, uint32_t shard_index, uint32_t shard_count);
+int ss_phase1_verification_vectors_shard_dev(const ss_phase1_params* p, const void* d_output, size_t output_len,
+                                             int compressed_output, void* d_new_challenge, size_t new_challenge_len,
+                                             int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                             const uint8_t* rho_seed, uint8_t* pairs, uint32_t shard_index,
+                                             uint32_t shard_count, void* stream);
+
+/* Bytes of a `pairs` blob (2 * (3 * g1_uncompressed + g2_uncompressed)), and the host-side reduction of SURVEY.md §8e:
+ * pairs <- element-wise group sums of `count` partial blobs laid out back to back.  The sum of the shards' partial
+ * (s, sx) is itself a valid random linear combination, so the caller's check_same_ratio runs on it unchanged. */
+size_t ss_phase1_pairs_size(int curve);
+int ss_phase1_reduce_partial_pairs(int curve, const uint8_t* partials, int count, uint8_t* pairs);
 
 /* -------------------------------------------------------------------------------------------- */
 /* prepare_phase2: powers of tau -> Lagrange coefficients                */
@@ -296,6 +340,12 @@ int ss_check_same_ratio_batch(int curve, const uint8_t* g1_pairs, const uint8_t*
 int ss_phase1_verification_ratios(const ss_phase1_params* p, const uint8_t* output, size_t output_len, int compressed_output,
                                   int check_output, uint8_t* new_challenge, size_t new_challenge_len,
                                   int compressed_new_challenge, int subgroup_mode, const uint8_t* rho_seed);
+
+/* check_power_ratios / check_power_ratios_g2 (phase1/src/helpers/accumulator.rs:56-91) of the four vectors from their
+ * (s, sx) `pairs` — whole-response pairs or the ss_phase1_reduce_partial_pairs of the shards' blobs — and
+ * g1_check = tau_g1[0] || tau_g1[1], g2_check = tau_g2[0] || tau_g2[1] (uncompressed, verification.rs:58-71).
+ * SS_ERR_INVALID_RATIO: ss_last_error().index = failing vector. */
+int ss_phase1_check_ratio_pairs(int curve, const uint8_t* pairs, const uint8_t* g1_check, const uint8_t* g2_check);
 
 /* -------------------------------------------------------------------------------------------- */
 /* phase-2 QAP evaluation                                                */

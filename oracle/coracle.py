@@ -25,6 +25,13 @@ def lib():
         L.oracle_powers.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.oracle_phase1_computation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64,
                                                 C.c_uint64, C.c_uint64, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.oracle_msm_pippenger.argtypes = L.oracle_msm.argtypes
+        L.oracle_verify_vector.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
+                                           C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_phase1_verification_vectors.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint64,
+                                                         C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_fq_mul_ns.restype = C.c_double
+        L.oracle_fq_mul_ns.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -113,3 +120,43 @@ def phase1_computation(curve, inp, out_len, cin, cout, check, n_g1, n_other, fir
     if rc:
         raise OracleError(rc, 0)
     return out.raw
+
+
+def msm_pippenger(curve, group, pts, compressed, n, scalars):
+    """VariableBaseMSM::msm_bigint restated (signed-digit bucket method, ark-ec 0.4.2) with explicit scalars."""
+    out = C.create_string_buffer(SIZES[(curve, group)][0])
+    rc = lib().oracle_msm_pippenger(curve, group, bytes(pts), int(compressed), n, b"".join(_s(curve, s) for s in scalars), out)
+    if rc:
+        raise OracleError(rc, 0)
+    return out.raw
+
+
+def phase1_verification_vectors(curve, resp, cin, out_len, cout, n_g1, n_other, seed=1, decode_passes=2, want_output=True):
+    """Per-vector loop of Phase1::verification as the reference runs it (decode twice, r*P subgroup test, power_pairs
+    with full-width random scalars, uncompressed re-emit).  Returns (new_challenge bytes | None, [(s, sx)] x 4)."""
+    out = C.create_string_buffer(out_len) if want_output else None
+    u1, u2 = SIZES[(curve, 0)][0], SIZES[(curve, 1)][0]
+    pairs = C.create_string_buffer(2 * (3 * u1 + u2))
+    bad = C.c_uint64(0)
+    rc = lib().oracle_phase1_verification_vectors(curve, bytes(resp), int(cin), out, int(cout), n_g1, n_other, seed,
+                                                  decode_passes, pairs, C.byref(bad))
+    if rc:
+        raise OracleError(rc, bad.value)
+    res, o = [], 0
+    for usz in (u1, u2, u1, u1):
+        res.append((pairs.raw[o:o + usz], pairs.raw[o + usz:o + 2 * usz]))
+        o += 2 * usz
+    return (out.raw if want_output else None), res
+
+
+def fq_mul_ns(iters=2000000):
+    """ns per BLS12-377 Fq Montgomery multiplication on one core (dependent chain)."""
+    return lib().oracle_fq_mul_ns(iters)
+
+
+def has_asm_mul():
+    return bool(lib().oracle_has_asm_mul())
+
+
+def force_portable_mul(on=True):
+    lib().oracle_force_portable_mul(int(on))

@@ -31,8 +31,13 @@
 #include <vector>
 
 #include "constants_gen.h"
+#include "mont_asm_gen.h"  // mulx / adcx / adox Montgomery product for 4- and 6-limb moduli (tools/gen_mont_asm.py)
 
 typedef unsigned __int128 u128;
+
+#if defined(ORACLE_MONT_ASM)
+static const bool kHaveAdx = __builtin_cpu_supports("adx") && __builtin_cpu_supports("bmi2");
+#endif
 
 namespace {
 
@@ -40,6 +45,9 @@ enum { E_OK = 0, E_INVALID_DATA = 1, E_UNEXPECTED_FLAGS = 2, E_POINT_AT_INFINITY
 enum { CHK_FULL = 0, CHK_NONZERO = 1, CHK_INGROUP = 2, CHK_NO = 3 };
 
 // ------------------------------------------------------------------------------------------------
+static bool g_force_portable = false;
+static inline bool force_portable() { return g_force_portable; }
+
 template <class P>
 struct Fp {
     static constexpr int N = P::N;
@@ -83,6 +91,17 @@ struct Fp {
     // CIOS Montgomery product, "no-carry" variant (valid because every modulus here leaves the top
     // bit of the top limb clear): the accumulator never exceeds N limbs.
     Fp operator*(const Fp& o) const {
+#if defined(ORACLE_MONT_ASM)
+        // same CIOS product through the two ADX carry chains — what LLVM makes of ark-ff's MontBackend (and what its
+        // `asm` feature hand-writes); the portable loop below is the fallback and the cross-check (tests)
+        if ((N == 4 || N == 6) && kHaveAdx && !force_portable()) {
+            Fp r;
+            if (N == 6) mont_mul_asm_6(r.v, v, o.v, P::MOD, P::INV);
+            else mont_mul_asm_4(r.v, v, o.v, P::MOD, P::INV);
+            if (geq_mod(r.v)) sub_mod(r.v);
+            return r;
+        }
+#endif
         uint64_t t[N];
 #pragma GCC unroll 16
         for (int j = 0; j < N; j++) t[j] = 0;
@@ -112,6 +131,7 @@ struct Fp {
     }
     Fp sqr() const { return *this * *this; }
     static constexpr int TWO_ADICITY_ = P::TWO_ADICITY;
+    static constexpr int BITS_ = P::BITS;
     static Fp fft_root() { Fp r; memcpy(r.v, P::FFT_ROOT, sizeof r.v); return r; }  // ark-ff TWO_ADIC_ROOT_OF_UNITY
     static Fp from_raw(const uint64_t* raw) { Fp a, r2; memcpy(a.v, raw, sizeof a.v); memcpy(r2.v, P::R2, sizeof r2.v); return a * r2; }
     void to_raw(uint64_t* out) const { Fp o = zero(); o.v[0] = 1; Fp c = *this * o; memcpy(out, c.v, sizeof c.v); }
@@ -510,6 +530,117 @@ int msm_naive(const uint8_t* pts, int compressed, size_t n, const uint8_t* scala
     return E_OK;
 }
 
+// ---- merge_pairs / power_pairs with the reference's MSM ---------------------------------------------------------
+// VariableBaseMSM::msm_bigint as ark-ec 0.4.2 runs it for short-Weierstrass points (negation is free, so the signed
+// "wNAF" bucket method): c = ln(n) + 2 (3 below 32 points), radix-2^c signed digits, one task per window, buckets
+// 1 .. 2^(c-1), running-sum bucket reduction, windows combined high to low with c doublings each.
+static inline size_t ln_without_floats(size_t a) {
+    size_t lg = 0;
+    while ((a >> (lg + 1)) != 0) lg++;
+    return lg * 69 / 100;
+}
+
+template <class G>
+Jac<typename G::F> msm_pippenger(const Aff<typename G::F>* pts, const uint64_t* scalars /*[n][FRL] canonical*/, size_t n, int num_bits) {
+    typedef typename G::F F;
+    const size_t c = n < 32 ? 3 : ln_without_floats(n) + 2;
+    const size_t digits_count = (num_bits + c - 1) / c;
+    const int64_t radix = (int64_t)1 << c, window_mask = radix - 1;
+    // make_digits: signed radix-2^c digits of every scalar
+    std::vector<int64_t> digits(n * digits_count);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t* k = scalars + i * G::FRL;
+        int64_t carry = 0;
+        for (size_t d = 0; d < digits_count; d++) {
+            const size_t bit = d * c, u = bit / 64, sh = bit % 64;
+            uint64_t bits = u < (size_t)G::FRL ? k[u] >> sh : 0;
+            if (sh + c > 64 && u + 1 < (size_t)G::FRL) bits |= k[u + 1] << (64 - sh);
+            int64_t coef = carry + (int64_t)(bits & (uint64_t)window_mask);
+            carry = (coef + radix / 2) >> c;
+            digits[i * digits_count + d] = coef - (carry << c);
+        }
+        digits[i * digits_count + digits_count - 1] += carry << c;
+    }
+    std::vector<Jac<F>> window_sums(digits_count);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t w = 0; w < digits_count; w++) {
+        std::vector<Jac<F>> buckets((size_t)1 << (c - 1), Jac<F>::identity());
+        for (size_t i = 0; i < n; i++) {
+            const int64_t d = digits[i * digits_count + w];
+            if (d > 0) buckets[d - 1] = jmadd(buckets[d - 1], pts[i]);
+            else if (d < 0) { Aff<F> m = pts[i]; m.y = m.y.neg(); buckets[-d - 1] = jmadd(buckets[-d - 1], m); }
+        }
+        Jac<F> run = Jac<F>::identity(), res = Jac<F>::identity();
+        for (size_t b = buckets.size(); b-- > 0;) { run = jadd(run, buckets[b]); res = jadd(res, run); }
+        window_sums[w] = res;
+    }
+    Jac<F> total = Jac<F>::identity();
+    for (size_t w = digits_count; w-- > 1;) {
+        total = jadd(total, window_sums[w]);
+        for (size_t k = 0; k < c; k++) total = jdbl(total);
+    }
+    return jadd(total, window_sums[0]);
+}
+
+static inline uint64_t splitmix64(uint64_t& x) {
+    uint64_t z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// One vector of the verification loop, as the reference runs it (phase1/src/verification.rs:243-411 with the whole
+// vector as one window): check_elements_are_nonzero_and_in_prime_order_subgroup (accumulator.rs:95-145: read_batch
+// with OnlyNonZero, then p.mul_bigint(r).is_zero() per element), check_power_ratios (accumulator.rs:56-91: a SECOND
+// read_batch of the same bytes, power_pairs = two msm_bigint over full-width random scalars, helpers.rs:371-390) and the
+// write_batch of the uncompressed elements (verification.rs:271-274).  The 2 pairings per vector are not included.
+template <class G>
+int verify_vector(const uint8_t* in, int in_c, uint8_t* out, int out_c, size_t n, int subgroup, int ratio, uint64_t seed,
+                  int decode_passes, uint8_t* s_out, uint8_t* sx_out, uint64_t* err_index) {
+    typedef typename G::F F; typedef typename G::Fr Fr;
+    const int isz = in_c ? G::CSIZE : G::USIZE, osz = out_c ? G::CSIZE : G::USIZE;
+    std::vector<Aff<F>> pts(n);
+    int err = 0; uint64_t bad = ~0ull;
+    for (int pass = 0; pass < (decode_passes < 1 ? 1 : decode_passes); pass++) {
+#pragma omp parallel for schedule(dynamic, 16)
+        for (size_t i = 0; i < n; i++) {
+            int e = decode<G>(in + i * isz, in_c != 0, CHK_NONZERO, pts[i]);
+            if (!e && pass == 0 && subgroup && !in_subgroup<G>(pts[i])) e = E_INCORRECT_SUBGROUP;
+            if (e) {
+#pragma omp critical
+                if (i < bad) { bad = i; err = e; }
+            }
+        }
+        if (err) { if (err_index) *err_index = bad; return err; }
+    }
+    if (ratio && n >= 2) {
+        const size_t m = n - 1;
+        std::vector<uint64_t> rho(m * G::FRL);
+        uint64_t st = seed;
+        const int top_bits = Fr::BITS_ - 64 * (G::FRL - 1);
+        for (size_t i = 0; i < m; i++) {  // Fr::rand: limbs masked to the modulus length, rejected when >= r
+            uint64_t* k = &rho[i * G::FRL];
+            do {
+                for (int j = 0; j < G::FRL; j++) k[j] = splitmix64(st);
+                if (top_bits < 64) k[G::FRL - 1] &= ((uint64_t)1 << top_bits) - 1;
+            } while (Fr::geq_mod(k));
+        }
+        Jac<F> res[2];
+        res[0] = msm_pippenger<G>(pts.data(), rho.data(), m, Fr::BITS_);
+        res[1] = msm_pippenger<G>(pts.data() + 1, rho.data(), m, Fr::BITS_);
+        std::vector<Jac<F>> two(res, res + 2); std::vector<Aff<F>> a;
+        normalize_batch(two, a);
+        encode<G>(s_out, false, a[0]);
+        encode<G>(sx_out, false, a[1]);
+    }
+    if (out) {
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n; i++) encode<G>(out + i * osz, out_c != 0, pts[i]);
+    }
+    return E_OK;
+}
+
 #define DISPATCH(curve, group, CALL)                 \
     do {                                             \
         if (curve == 0 && group == 0) return CALL(BlsG1); \
@@ -591,6 +722,80 @@ int oracle_phase1_computation(int curve, const uint8_t* in, uint8_t* out, int ci
     // beta_g2 <- beta * beta_g2: tau^0 * beta
     uint8_t one[48] = {1};
     return oracle_apply_powers(curve, 1, in + oi, cin, check, out + oo, cout, 1, nullptr, one, 0, beta, &bad);
+}
+
+// merge of the two: explicit-scalar Pippenger MSM (pins msm_pippenger against the naive sum in tests)
+int oracle_msm_pippenger(int curve, int group, const uint8_t* pts, int compressed, size_t n, const uint8_t* scalars, uint8_t* out) {
+#define CALL(G) ([&]() -> int {                                                                      \
+        typedef typename G::F F;                                                                     \
+        const int isz = compressed ? G::CSIZE : G::USIZE;                                            \
+        std::vector<Aff<F>> p(n);                                                                    \
+        for (size_t i = 0; i < n; i++) { int e = decode<G>(pts + i * isz, compressed != 0, CHK_NO, p[i]); if (e) return e; } \
+        std::vector<uint64_t> k(n * G::FRL);                                                         \
+        memcpy(k.data(), scalars, n * G::FRL * 8);                                                   \
+        std::vector<Jac<F>> one(1, msm_pippenger<G>(p.data(), k.data(), n, G::Fr::BITS_));          \
+        std::vector<Aff<F>> a;                                                                       \
+        normalize_batch(one, a);                                                                     \
+        encode<G>(out, false, a[0]);                                                                 \
+        return 0; })()
+    DISPATCH(curve, group, CALL);
+#undef CALL
+}
+
+int oracle_verify_vector(int curve, int group, const uint8_t* in, int in_c, uint8_t* out, int out_c, size_t n, int subgroup,
+                         int ratio, uint64_t seed, int decode_passes, uint8_t* s_out, uint8_t* sx_out, uint64_t* err_index) {
+#define CALL(G) verify_vector<G>(in, in_c, out, out_c, n, subgroup, ratio, seed, decode_passes, s_out, sx_out, err_index)
+    DISPATCH(curve, group, CALL);
+#undef CALL
+}
+
+// The per-vector loop of Phase1::verification over a whole Groth16 response (phase1/src/verification.rs:217-411):
+// tau_g1, tau_g2, alpha_g1, beta_g1 through verify_vector, beta_g2 read with Full and re-emitted (:199-201).
+// `pairs`: 4 x (s || sx) uncompressed like ss_phase1_verification_vectors.
+int oracle_phase1_verification_vectors(int curve, const uint8_t* in, int cin, uint8_t* out, int cout, uint64_t n_g1,
+                                       uint64_t n_other, uint64_t seed, int decode_passes, uint8_t* pairs, uint64_t* err_index) {
+    const int g1u = curve == 0 ? 96 : 192, g1c = curve == 0 ? 48 : 96, g2u = 192, g2c = 96;
+    const size_t s1i = cin ? g1c : g1u, s2i = cin ? g2c : g2u, s1o = cout ? g1c : g1u, s2o = cout ? g2c : g2u;
+    const uint64_t cnt[4] = {n_g1, n_other, n_other, n_other};
+    const int grp[4] = {0, 1, 0, 0};
+    size_t oi = 64, oo = 64, po = 0;
+    int e;
+    for (int v = 0; v < 4; v++) {
+        const size_t usz = grp[v] ? g2u : g1u;
+        if (cnt[v]) {
+            e = oracle_verify_vector(curve, grp[v], in + oi, cin, out ? out + oo : nullptr, cout, cnt[v], 1, cnt[v] >= 2, seed + v,
+                                     decode_passes, pairs + po, pairs + po + usz, err_index);
+            if (e) return e;
+        }
+        oi += cnt[v] * (grp[v] ? s2i : s1i);
+        oo += cnt[v] * (grp[v] ? s2o : s1o);
+        po += 2 * usz;
+    }
+    return oracle_transcode(curve, 1, in + oi, cin, CHK_FULL, out ? out + oo : nullptr, cout, 1, 0, err_index);
+}
+
+void oracle_force_portable_mul(int on) { g_force_portable = on != 0; }
+int oracle_has_asm_mul(void) {
+#if defined(ORACLE_MONT_ASM)
+    return kHaveAdx ? 1 : 0;
+#else
+    return 0;
+#endif
+}
+
+// ns per Montgomery multiplication of the BLS12-377 base field on one core (dependent chain), printed beside `cores`
+double oracle_fq_mul_ns(int iters) {
+    typedef Fp<OBls377Fq> F;
+    F a = F::one() + F::one(), b;
+    memcpy(b.v, kO_bls_g1_b, sizeof b.v);
+    b = b + b + b;
+    a = a * b + b;
+    const double t0 = omp_get_wtime();
+    for (int i = 0; i < iters; i++) a = a * b;
+    const double t1 = omp_get_wtime();
+    volatile uint64_t sink = a.v[0];
+    (void)sink;
+    return (t1 - t0) * 1e9 / iters;
 }
 
 }  // extern "C"

@@ -174,6 +174,9 @@ struct Lane {
 };
 std::vector<Lane*> g_lanes;
 
+// ss_set_strict_unchecked_inputs: bases read without a subgroup check go through the reference's double-and-add
+// instead of GLV / GLS (which presuppose the order-r subgroup), glv.cuh
+std::atomic<int> g_strict_unchecked{0};
 std::atomic<int> g_concurrent{-1};  // -1: take $SS_CONCURRENT_VECTORS (default on)
 bool concurrent_vectors() {
     int v = g_concurrent.load();
@@ -230,6 +233,8 @@ int lane_acquire(int device, size_t bytes, Lane** out) {
         }
         ln->busy = true;
     }
+    // the caller's LaneGuard owns the lane from here on, so every error path below releases it
+    *out = ln;
     CU(cudaSetDevice(device));
     if (!ln->stream) CU(cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
     if (ln->cap < bytes) {
@@ -239,7 +244,6 @@ int lane_acquire(int device, size_t bytes, Lane** out) {
         CU(cudaMalloc(&ln->buf, bytes));
         ln->cap = bytes;
     }
-    *out = ln;
     return SS_OK;
 }
 
@@ -384,6 +388,7 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
         a.coeff_m = j.d_coeff_m;
         a.has_coeff = j.has_coeff;
         a.jac = jac;
+        a.plain_ladder = (g_strict_unchecked.load() && (j.check == SS_CHECK_NO || j.check == SS_CHECK_ONLY_NON_ZERO)) ? 1 : 0;
         { ProfScope ps("k_scalar_mul", o.name, cnt, s); o.scalar_mul(a, s); }
         NormalizeArgs na;
         na.jac = jac;
@@ -456,6 +461,19 @@ bool scalar_is_canonical(int curve, const uint8_t* s) {
     return false;
 }
 
+// [start, end) of part `part` of `parts` equal contiguous parts of n elements (the first n % parts parts get one more)
+void part_range(uint64_t n, uint64_t part, uint64_t parts, uint64_t* s0, uint64_t* e0) {
+    const uint64_t base = n / parts, rem = n % parts;
+    *s0 = part * base + std::min<uint64_t>(part, rem);
+    *e0 = *s0 + base + (part < rem ? 1 : 0);
+}
+
+// Marlin's short tau_g2 / alpha_g1 vectors live in the buffer of chunk_index 0 — the ONE predicate the reference uses for
+// the sizes (parameters.rs:152-160), the buffer split (buffers.rs:151,220,274,324) and the computation
+// (computation.rs:198); full-mode callers pass chunk_index = 0.  Sizes, computation, verification and
+// initialization here all go through this function so they cannot disagree about the buffer layout.
+bool is_chunk0(const ss_phase1_params* p) { return p->chunk_index == 0; }
+
 int phase1_sizes(const ss_phase1_params* p, ss_phase1_sizes* o) {
     if (!p || !o) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
     const GroupOps* g1 = group_ops(p->curve, SS_G1);
@@ -489,7 +507,7 @@ int phase1_sizes(const ss_phase1_params* p, ss_phase1_sizes* o) {
         o->contribution_size = o->g1_chunk_size * g1->csize + o->other_chunk_size * (g2->csize + 2 * (uint64_t)g1->csize) + g2->csize + 64 + o->public_key_size;
     } else {
         uint64_t xu = 0, xc = 0;
-        if (p->chunk_index == 0) {
+        if (is_chunk0(p)) {
             xu = 3 * (uint64_t)g1->usize + 3 * k * g1->usize + (k + 2) * g2->usize;
             xc = 3 * (uint64_t)g1->csize + 3 * k * g1->csize + (k + 2) * g2->csize;
         }
@@ -504,7 +522,8 @@ int phase1_sizes(const ss_phase1_params* p, ss_phase1_sizes* o) {
 // powers etc.) are produced by k_marlin_scalars and applied through the explicit-exponent path.
 int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& z, const GroupOps& g1, const GroupOps& g2,
                               const uint8_t* input, size_t input_len, uint8_t* output, size_t output_len, int cin, int cout,
-                              int check, const uint8_t* tau, const uint8_t* alpha, bool host, cudaStream_t user_stream) {
+                              int check, const uint8_t* tau, const uint8_t* alpha, bool host, cudaStream_t user_stream,
+                              uint32_t shard_index, uint32_t shard_count) {
     const uint64_t need_in = cin ? z.contribution_size - z.public_key_size : z.accumulator_size;
     const uint64_t need_out = cout ? z.contribution_size - z.public_key_size : z.accumulator_size;
     if (input_len < need_in) return fail(SS_ERR_INVALID_LENGTH, 0, need_in, input_len, "input buffer too short");
@@ -516,7 +535,7 @@ int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& 
     const int device = g_devices[0];
     CU(cudaSetDevice(device));
     const uint64_t k = p->total_size_in_log2;
-    const bool chunk0 = p->chunk_index == 0 || p->contribution_mode == SS_MODE_FULL;
+    const bool chunk0 = is_chunk0(p);
     const uint64_t n_g2 = chunk0 ? k + 2 : 0, n_al = chunk0 ? 3 + 3 * k : 0;
     auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
     LaneGuard lane;
@@ -526,9 +545,16 @@ int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& 
     if ((rc = sc.init(g1, tau, coeffs, lane.l->stream))) return rc;
     const uint64_t first = p->contribution_mode == SS_MODE_CHUNKED ? p->chunk_index * p->chunk_size : 0;
     const uint64_t n1 = z.g1_chunk_size;
-    VectorJob jt = {&g1, input + 64, output + 64, cin, cout, check, n1, nullptr, sc.d_tab, first, sc.d_coeff_m[0], 0, "tau_g1"};
-    if ((rc = run_vector_on(device, jt, host, user_stream))) return rc;
-    if (!chunk0) return SS_OK;
+    // index-range shard of tau_g1 (the short tau_g2 / alpha_g1 vectors belong to shard 0)
+    uint64_t s0, e0;
+    part_range(n1, shard_index, shard_count, &s0, &e0);
+    VectorJob jt = {&g1, input + 64 + s0 * sz(g1, cin), output + 64 + s0 * sz(g1, cout), cin, cout, check, e0 - s0, nullptr,
+                    sc.d_tab, first + s0, sc.d_coeff_m[0], 0, "tau_g1"};
+    if ((rc = run_vector_on(device, jt, host, user_stream))) {
+        g_err.index += s0;
+        return rc;
+    }
+    if (!chunk0 || shard_index != 0) return SS_OK;
     uint8_t* d_g2s = lane.l->buf;
     uint8_t* d_als = d_g2s + align_up(n_g2 * g1.fr_bytes, 256);
     g1.marlin_scalars(sc.d_tab, z.powers_length, (int)k, reinterpret_cast<uint32_t*>(d_g2s), reinterpret_cast<uint32_t*>(d_als),
@@ -547,9 +573,12 @@ int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& 
 
 int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
                             size_t output_len, int cin, int cout, int check, const uint8_t* tau,
-                            const uint8_t* alpha, const uint8_t* beta, bool host, cudaStream_t user_stream) {
+                            const uint8_t* alpha, const uint8_t* beta, bool host, cudaStream_t user_stream,
+                            uint32_t shard_index = 0, uint32_t shard_count = 1) {
     if (!p || !input || !output || !tau || !alpha || (!beta && p->proving_system != SS_MARLIN))
         return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (shard_count == 0 || shard_index >= shard_count)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "shard %u of %u", shard_index, shard_count);
     if (check < 0 || check > 3) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad check mode %d", check);
     ss_phase1_sizes z;
     int rc = phase1_sizes(p, &z);
@@ -558,7 +587,7 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
     const GroupOps& g2 = *group_ops(p->curve, SS_G2);
     if (p->proving_system == SS_MARLIN)
         return phase1_computation_marlin(p, z, g1, g2, input, input_len, output, output_len, cin, cout, check, tau, alpha, host,
-                                         user_stream);
+                                         user_stream, shard_index, shard_count);
     const uint64_t need_in = cin ? z.contribution_size - z.public_key_size : z.accumulator_size;
     const uint64_t need_out = cout ? z.contribution_size - z.public_key_size : z.accumulator_size;
     if (input_len < need_in) return fail(SS_ERR_INVALID_LENGTH, 0, need_in, input_len, "input buffer too short");
@@ -584,10 +613,12 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
     }
     const uint64_t first = p->contribution_mode == SS_MODE_CHUNKED ? p->chunk_index * p->chunk_size : 0;
 
-    // One worker per device.  Every vector is cut into D equal contiguous parts (balance by
-    // work, not by index — indices >= 2^k only carry one G1 element); element i of a part still gets
-    // tau^(first + i) because each part passes its own first power.  No inter-device traffic.
+    // One worker per device.  Every vector is cut into shard_count * D equal contiguous parts (SURVEY.md §8e:
+    // balance by work, not by index — indices >= 2^k only carry one G1 element); this call owns parts
+    // [shard_index * D, (shard_index + 1) * D), one per device.  Element i of a part still gets tau^(first + i)
+    // because each part passes its own first power.  No inter-device / inter-process traffic.
     const int D = host ? (int)g_devices.size() : 1;
+    const uint64_t parts = (uint64_t)shard_count * D;
     auto worker = [&](int di, ss_error_info* err) -> int {
         const int device = host ? g_devices[di] : g_devices[0];
         auto run = [&]() -> int {
@@ -606,11 +637,10 @@ int phase1_computation_impl(const ss_phase1_params* p, const uint8_t* input, siz
             auto one_vector = [&](int v) -> int {
                 uint64_t s0 = 0, e0 = cnt[v];
                 if (v == 4) {
-                    if (di != 0) return SS_OK;  // beta_g2 <- beta * beta_g2 (computation.rs:42-50): tau^0 * beta
+                    // beta_g2 <- beta * beta_g2 (computation.rs:42-50): tau^0 * beta, by the owner of part 0
+                    if (di != 0 || shard_index != 0) return SS_OK;
                 } else {
-                    const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
-                    s0 = di * base + std::min<uint64_t>(di, rem);
-                    e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
+                    part_range(cnt[v], (uint64_t)shard_index * D + di, parts, &s0, &e0);
                 }
                 VectorJob job = {gs[v], input + oi[v] + s0 * sz(*gs[v], cin), output + oo[v] + s0 * sz(*gs[v], cout), cin,
                                  cout, check, e0 - s0, nullptr, sc.d_tab, v == 4 ? 0 : first + s0, cm[v], hc[v], names[v]};
@@ -723,6 +753,8 @@ int ss_profile_read(ss_profile_entry* out, int max_entries) {
 }
 
 void ss_set_concurrent_vectors(int on) { g_concurrent.store(on ? 1 : 0); }
+
+void ss_set_strict_unchecked_inputs(int on) { g_strict_unchecked.store(on ? 1 : 0); }
 
 int ss_device_count(void) {
     int c = 0;
@@ -850,7 +882,7 @@ static int transcode_impl(int curve, int group, const uint8_t* in, int in_compre
         DecodeArgs da = {reinterpret_cast<const uint32_t*>(bi), in_compressed, check, cnt, aff, inf, d_status};
         { ProfScope ps("k_decode", o->name, cnt, s); o->decode(da, s); }
         if (rmul_subgroup) {
-            SubgroupArgs sa = {aff, inf, cnt, d_status + 1, cnt};
+            SubgroupArgs sa = {aff, inf, cnt, d_status + 1, cnt, in_compressed ? 0 : 1};
             ProfScope ps("k_subgroup", o->name, cnt, s);
             o->subgroup(sa, s);
         }
@@ -993,10 +1025,22 @@ int ss_phase1_initialization(const ss_phase1_params* p, uint8_t* output, size_t 
     if (rc) return rc;
     const GroupOps* gs[2] = {group_ops(p->curve, SS_G1), group_ops(p->curve, SS_G2)};
     const uint64_t s1 = compressed_output ? gs[0]->csize : gs[0]->usize, s2 = compressed_output ? gs[1]->csize : gs[1]->usize;
-    uint64_t off[5];
-    vector_offsets(p->curve, z, compressed_output, off);
-    const bool has_beta_g2 = true;  // every chunk buffer carries a beta_g2 slot (parameters.rs get_length) and init_element fills it
-    const uint64_t need = off[4] + s2;
+    // split_mut (buffers.rs:246-288): Groth16 = [tau_g1][tau_g2][alpha_g1][beta_g1][beta_g2]; Marlin = [tau_g1] and, in the
+    // buffer of chunk 0, [tau_g2 x (k+2)][alpha_g1 x (3+3k)] — no beta_g1 / beta_g2 slots at all.
+    const bool marlin = p->proving_system == SS_MARLIN;
+    if (!marlin && p->proving_system != SS_GROTH16)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown proving system %d", p->proving_system);
+    const uint64_t mk = p->total_size_in_log2;
+    const uint64_t cnt[5] = {z.g1_chunk_size,
+                             marlin ? (is_chunk0(p) ? mk + 2 : 0) : z.other_chunk_size,
+                             marlin ? (is_chunk0(p) ? 3 + 3 * mk : 0) : z.other_chunk_size,
+                             marlin ? 0 : z.other_chunk_size,
+                             marlin ? 0u : 1u};
+    const int grp[5] = {0, 1, 0, 0, 1};
+    uint64_t off[6];
+    off[0] = 64;
+    for (int v = 0; v < 5; v++) off[v + 1] = off[v] + cnt[v] * (grp[v] ? s2 : s1);
+    const uint64_t need = off[5];
     if (output_len < need) return fail(SS_ERR_INVALID_LENGTH, 0, need, output_len, "output buffer too short");
     if ((rc = ensure_init())) return rc;
     LaneGuard lg;
@@ -1017,11 +1061,7 @@ int ss_phase1_initialization(const ss_phase1_params* p, uint8_t* output, size_t 
             done += k;
         }
     };
-    fill(output + off[0], gen[0], s1, z.g1_chunk_size);
-    fill(output + off[1], gen[1], s2, z.other_chunk_size);
-    fill(output + off[2], gen[0], s1, z.other_chunk_size);
-    fill(output + off[3], gen[0], s1, z.other_chunk_size);
-    if (has_beta_g2) fill(output + off[4], gen[1], s2, 1);
+    for (int v = 0; v < 5; v++) fill(output + off[v], gen[grp[v]], grp[v] ? s2 : s1, cnt[v]);
     return SS_OK;
 }
 
@@ -1077,6 +1117,28 @@ int ss_phase1_computation_dev(const ss_phase1_params* p, const void* d_input, si
     return phase1_computation_impl(p, static_cast<const uint8_t*>(d_input), input_len, static_cast<uint8_t*>(d_output),
                                    output_len, compressed_input, compressed_output, check_input, tau, alpha, beta,
                                    false, static_cast<cudaStream_t>(stream));
+}
+
+// Index-range shard of ONE ceremony: every vector of the challenge is cut into `shard_count` equal
+// contiguous parts and this call processes part `shard_index` (element i of the vector still gets tau^(first + i)).
+// `input` / `output` are the WHOLE challenge / response buffers — typically the same file mapped by every
+// process — and only the shard's byte ranges are read and written, the contract the reference's sibling tasks
+// already rely on (computation.rs:82-186).  beta_g2 belongs to shard 0.  No inter-process traffic.
+int ss_phase1_computation_shard(const ss_phase1_params* p, const uint8_t* input, size_t input_len, uint8_t* output,
+                                size_t output_len, int compressed_input, int compressed_output, int check_input,
+                                const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t shard_index,
+                                uint32_t shard_count) {
+    return phase1_computation_impl(p, input, input_len, output, output_len, compressed_input, compressed_output,
+                                   check_input, tau, alpha, beta, true, nullptr, shard_index, shard_count);
+}
+
+int ss_phase1_computation_shard_dev(const ss_phase1_params* p, const void* d_input, size_t input_len, void* d_output,
+                                    size_t output_len, int compressed_input, int compressed_output, int check_input,
+                                    const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t shard_index,
+                                    uint32_t shard_count, void* stream) {
+    return phase1_computation_impl(p, static_cast<const uint8_t*>(d_input), input_len, static_cast<uint8_t*>(d_output),
+                                   output_len, compressed_input, compressed_output, check_input, tau, alpha, beta,
+                                   false, static_cast<cudaStream_t>(stream), shard_index, shard_count);
 }
 
 }  // extern "C"

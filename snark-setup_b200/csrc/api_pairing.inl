@@ -79,6 +79,36 @@ int ss_check_same_ratio_batch(int curve, const uint8_t* g1_pairs, const uint8_t*
     return SS_OK;
 }
 
+// check_power_ratios / check_power_ratios_g2 (phase1/src/helpers/accumulator.rs:56-91) for the four vectors of a
+// response, given their (s, sx) `pairs` (ss_phase1_verification_vectors, or the ss_phase1_reduce_partial_pairs of the
+// shards' partial blobs) and g1_check = (tau_g1[0], tau_g1[1]), g2_check = (tau_g2[0], tau_g2[1]), uncompressed
+// (verification.rs:58-71): tau_g1 / alpha_g1 / beta_g1 powers against g2_check, tau_g2 powers against g1_check, the
+// four check_same_ratio in one launch.  SS_ERR_INVALID_RATIO: index = 0 tau_g1, 1 tau_g2, 2 alpha_g1, 3 beta_g1.
+int ss_phase1_check_ratio_pairs(int curve, const uint8_t* pairs, const uint8_t* g1_check, const uint8_t* g2_check) {
+    const GroupOps* g1 = group_ops(curve, SS_G1);
+    const GroupOps* g2 = group_ops(curve, SS_G2);
+    if (!g1 || !g2) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve");
+    if (!pairs || !g1_check || !g2_check) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    const size_t u1 = g1->usize, u2 = g2->usize;
+    std::vector<uint8_t> a(4 * 2 * u1), b(4 * 2 * u2);
+    const uint8_t* pr = pairs;
+    memcpy(a.data(), pr, 2 * u1);
+    memcpy(b.data(), g2_check, 2 * u2);
+    memcpy(a.data() + 2 * u1, g1_check, 2 * u1);
+    memcpy(b.data() + 2 * u2, pr + 2 * u1, 2 * u2);
+    memcpy(a.data() + 4 * u1, pr + 2 * u1 + 2 * u2, 2 * u1);
+    memcpy(b.data() + 4 * u2, g2_check, 2 * u2);
+    memcpy(a.data() + 6 * u1, pr + 4 * u1 + 2 * u2, 2 * u1);
+    memcpy(b.data() + 6 * u2, g2_check, 2 * u2);
+    int bad = -1;
+    int rc = ss_check_same_ratio_batch(curve, a.data(), b.data(), 4, &bad);
+    if (rc == SS_ERR_INVALID_RATIO) {
+        static const char* names[4] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1"};
+        return fail(SS_ERR_INVALID_RATIO, (uint64_t)bad, 0, 0, "Invalid ratio! Context: Power pairs: %s", names[bad & 3]);
+    }
+    return rc;
+}
+
 // The per-vector half of Phase1::verification with its verdict (phase1/src/verification.rs:44-80,217-411):
 // ss_phase1_verification_vectors, then check_power_ratios / check_power_ratios_g2 of every vector
 // (phase1/src/helpers/accumulator.rs:56-91) against g2_check = (tau_g2[0], tau_g2[1]) resp.
@@ -105,24 +135,7 @@ int ss_phase1_verification_ratios(const ss_phase1_params* p, const uint8_t* outp
     // read_initial_elements (verification.rs:58-65)
     if ((rc = ss_transcode(p->curve, SS_G1, output + off[0], compressed_output, check_output, g1_check.data(), 0, 2))) return rc;
     if ((rc = ss_transcode(p->curve, SS_G2, output + off[1], compressed_output, check_output, g2_check.data(), 0, 2))) return rc;
-    std::vector<uint8_t> a(4 * 2 * u1), b(4 * 2 * u2);
-    const uint8_t* pr = pairs.data();
-    // tau_g1 powers vs g2_check; tau_g2 powers vs g1_check; alpha_g1, beta_g1 powers vs g2_check
-    memcpy(a.data(), pr, 2 * u1);
-    memcpy(b.data(), g2_check.data(), 2 * u2);
-    memcpy(a.data() + 2 * u1, g1_check.data(), 2 * u1);
-    memcpy(b.data() + 2 * u2, pr + 2 * u1, 2 * u2);
-    memcpy(a.data() + 4 * u1, pr + 2 * u1 + 2 * u2, 2 * u1);
-    memcpy(b.data() + 4 * u2, g2_check.data(), 2 * u2);
-    memcpy(a.data() + 6 * u1, pr + 4 * u1 + 2 * u2, 2 * u1);
-    memcpy(b.data() + 6 * u2, g2_check.data(), 2 * u2);
-    int bad = -1;
-    rc = ss_check_same_ratio_batch(p->curve, a.data(), b.data(), 4, &bad);
-    if (rc == SS_ERR_INVALID_RATIO) {
-        static const char* names[4] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1"};
-        return fail(SS_ERR_INVALID_RATIO, (uint64_t)bad, 0, 0, "Invalid ratio! Context: Power pairs: %s", names[bad & 3]);
-    }
-    return rc;
+    return ss_phase1_check_ratio_pairs(p->curve, pairs.data(), g1_check.data(), g2_check.data());
 }
 
 }  // extern "C"

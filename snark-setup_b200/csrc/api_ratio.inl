@@ -177,7 +177,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
             // only the first `own` elements: the overlap element belongs to the next tile.  The SoA
             // stride is `ne`, so pass n = own through a strided view: k_subgroup indexes [i] with stride n,
             // hence it is launched over `ne` with the count check inside the kernel args.
-            SubgroupArgs sa = {aff1, inf1, stride, d_status + 2 * t + 1, own};
+            SubgroupArgs sa = {aff1, inf1, stride, d_status + 2 * t + 1, own, j.compressed ? 0 : 1};
             ProfScope ps("k_subgroup", o.name, own, s);
             o.subgroup(sa, s);
         }
@@ -252,6 +252,55 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     return SS_OK;
 }
 
+// pairs <- element-wise sums of `count` blobs laid out like the `pairs` output of ss_phase1_verification_vectors
+// (4 x (s || sx), uncompressed: G1, G2, G1, G1).  Identity slots (0x40 flag) are neutral.  Eight tiny kernels on
+// one stream, one synchronisation.
+int sum_pair_blobs(int curve, const uint8_t* const* blobs, int count, uint8_t* pairs) {
+    const GroupOps* g1 = group_ops(curve, SS_G1);
+    const GroupOps* g2 = group_ops(curve, SS_G2);
+    if (!g1 || !g2) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve %d", curve);
+    if (count <= 0 || !blobs || !pairs) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    const GroupOps* gs[4] = {g1, g2, g1, g1};
+    const size_t blob_b = 2 * (3 * (size_t)g1->usize + g2->usize);
+    const int dev0 = g_devices[0];
+    CU(cudaSetDevice(dev0));
+    LaneGuard lg;
+    const size_t in_b = align_up((size_t)count * blob_b, 256);
+    if ((rc = lane_acquire(dev0, 256 + in_b + align_up(blob_b, 256), &lg.l))) return rc;
+    cudaStream_t s = lg.l->stream;
+    unsigned long long* d_status = reinterpret_cast<unsigned long long*>(lg.l->buf);
+    uint8_t* d_in = lg.l->buf + 256;
+    uint8_t* d_out = d_in + in_b;
+    // stage: for every (vector, half) the `count` points contiguously
+    std::vector<uint8_t> stage((size_t)count * blob_b);
+    size_t off = 0, slot_off[8], src_off = 0;
+    for (int v = 0; v < 4; v++)
+        for (int half = 0; half < 2; half++) {
+            const size_t usz = gs[v]->usize;
+            slot_off[2 * v + half] = off;
+            for (int k = 0; k < count; k++) memcpy(stage.data() + off + k * usz, blobs[k] + src_off, usz);
+            off += (size_t)count * usz;
+            src_off += usz;
+        }
+    CU(cudaMemsetAsync(d_status, 0xff, 8, s));
+    CU(cudaMemcpyAsync(d_in, stage.data(), stage.size(), cudaMemcpyHostToDevice, s));
+    src_off = 0;
+    for (int v = 0; v < 4; v++)
+        for (int half = 0; half < 2; half++) {
+            gs[v]->sum_points(reinterpret_cast<const uint32_t*>(d_in + slot_off[2 * v + half]), count,
+                              reinterpret_cast<uint32_t*>(d_out + src_off), d_status, s);
+            src_off += gs[v]->usize;
+        }
+    CU(cudaGetLastError());
+    unsigned long long st;
+    CU(cudaMemcpyAsync(pairs, d_out, blob_b, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&st, d_status, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return decode_status(st, 0, "sum of partial ratio points");
+}
+
 int ratio_common_checks(int curve, int group, const void* v, size_t n, int check) {
     if (!group_ops(curve, group)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown curve/group %d/%d", curve, group);
     if (n && !v) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null input");
@@ -309,8 +358,11 @@ int ss_check_and_ratio(int curve, int group, const uint8_t* in, int in_compresse
 static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
                                     int compressed_output, uint8_t* new_challenge, size_t new_challenge_len,
                                     int compressed_new_challenge, int subgroup_mode, int ratio_check,
-                                    const uint8_t* rho_seed, uint8_t* pairs, bool host, cudaStream_t stream) {
+                                    const uint8_t* rho_seed, uint8_t* pairs, bool host, cudaStream_t stream,
+                                    uint32_t shard_index = 0, uint32_t shard_count = 1) {
     if (!p || !output) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "null argument");
+    if (shard_count == 0 || shard_index >= shard_count)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "shard %u of %u", shard_index, shard_count);
     if (p->proving_system != SS_GROTH16 && p->proving_system != SS_MARLIN)
         return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "unknown proving system %d", p->proving_system);
     if (ratio_check && (!rho_seed || !pairs)) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "ratio check needs rho_seed and pairs");
@@ -329,7 +381,7 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
     // Marlin (verification.rs:413-483): tau_g1 over the chunk, plus k+2 tau_g2 and 3+3k alpha_g1 elements on chunk 0;
     // only tau_g1 is a power sequence (its ratio is what aggregate_verification checks, :649-672)
     const bool marlin = p->proving_system == SS_MARLIN;
-    const bool chunk0 = p->chunk_index == 0 || p->contribution_mode == SS_MODE_FULL;
+    const bool chunk0 = is_chunk0(p);
     const uint64_t mk = p->total_size_in_log2;
     const uint64_t cnt[5] = {n1, marlin ? (chunk0 ? mk + 2 : 0) : n2, marlin ? (chunk0 ? 3 + 3 * mk : 0) : n2, marlin ? 0 : n2,
                              marlin ? 0u : 1u};
@@ -353,31 +405,43 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
         // a vector of one element cannot be ratio-checked (verification.rs:238-241 -> BatchTooSmall)
         if (ratio_check && has_ratio[v] && cnt[v] == 1) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: batch too small", names[v]);
 
-    // One worker per device: device d takes the d-th contiguous part of every vector (plus one element of
-    // overlap for the ratio pairs, helpers.rs:388-390) and produces partial (s, sx); rho_i is indexed by
-    // the GLOBAL element index so the shards of one vector use disjoint ChaCha20 blocks.  The <= D partial
-    // points per vector are added on device 0 (k_sum_points); no other inter-device traffic.
+    // One worker per device: every vector is cut into shard_count * D contiguous parts, this call owns parts
+    // [shard_index * D, (shard_index + 1) * D), one per device; a part reads one element of overlap for the ratio
+    // pairs that continue into the next part (helpers.rs:388-390) and produces partial (s, sx); rho_i is indexed
+    // by the GLOBAL element index so the parts of one vector use disjoint ChaCha20 blocks.  The <= D partial
+    // points per vector are added on device 0 (k_sum_points); no other inter-device traffic.  With shard_count > 1
+    // `pairs` receives this shard's PARTIAL sums (ss_phase1_reduce_partial_pairs adds the shards' blobs).
     const int D = host ? (int)g_devices.size() : 1;
+    const uint64_t parts = (uint64_t)shard_count * D;
     std::vector<std::vector<uint8_t>> partial(D);
+    // every partial slot starts as the identity encoding (all-zero bytes would decode as the finite point (0, 0))
+    auto identity_pairs = [&](std::vector<uint8_t>& blob) {
+        blob.assign(2 * (3 * (size_t)g1.usize + g2.usize), 0);
+        for (int v = 0; v < 4; v++) {
+            blob[op[v] + gs[v]->usize - 1] = 0x40;
+            blob[op[v] + 2 * gs[v]->usize - 1] = 0x40;
+        }
+    };
+    for (int di = 0; di < D; di++) identity_pairs(partial[di]);
     auto worker = [&](int di, ss_error_info* err) -> int {
         const int device = host ? g_devices[di] : g_devices[0];
-        partial[di].assign(2 * (3 * (size_t)g1.usize + g2.usize), 0);
         auto one_vector = [&](int v) -> int {
             if (!cnt[v]) return SS_OK;
             cudaStream_t st = concurrent_vectors() ? nullptr : stream;
             uint8_t* out = new_challenge ? new_challenge + ob[v] : nullptr;
             int r;
             if (v == 4) {
-                if (di != 0 || !out) return SS_OK;
-                // beta_g2: read with check_output_for_correctness (Full by default) and re-emit
+                if (di != 0 || shard_index != 0) return SS_OK;
+                // beta_g2: ALWAYS read with check_output_for_correctness (Full by default, verification.rs:199-201),
+                // re-emitted only when there is a new challenge
                 RatioJob j = {p->curve, grp[v], output + oa[v], nullptr, compressed_output, SS_CHECK_FULL, 1, 0, 0, nullptr,
                               nullptr, out, compressed_new_challenge, nullptr, nullptr, names[v]};
                 return run_ratio_vector(device, j, host, st);
             }
             // own elements [s0, e0); read one more when pairs continue into the next shard
-            const uint64_t base = cnt[v] / D, rem = cnt[v] % D;
-            const uint64_t s0 = di * base + std::min<uint64_t>(di, rem), e0 = s0 + base + ((uint64_t)di < rem ? 1 : 0);
-            if (e0 == s0) return SS_OK;
+            uint64_t s0, e0;
+            part_range(cnt[v], (uint64_t)shard_index * D + di, parts, &s0, &e0);
+            if (e0 == s0) return SS_OK;  // empty part: its partial stays the identity
             const bool last = e0 == cnt[v];
             const bool want_ratio = ratio_check && has_ratio[v];
             const uint64_t nread = (e0 - s0) + ((want_ratio && !last) ? 1 : 0);
@@ -392,12 +456,7 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
                 g_err.index += s0;
                 return r;
             }
-            if (!do_ratio) {  // a one-element tail shard contributes the identity
-                memset(ps, 0, 2 * (size_t)gs[v]->usize);
-                ps[gs[v]->usize - 1] = 0x40;
-                ps[2 * gs[v]->usize - 1] = 0x40;
-            }
-            return SS_OK;
+            return SS_OK;  // a part without a pair (one-element tail) leaves the identity in its slot
         };
         auto run = [&]() -> int {
             if (!concurrent_vectors()) {
@@ -448,31 +507,9 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
             return rcs[di];
         }
     if (!ratio_check || !pairs) return SS_OK;
-    // add the partial sums on device 0
-    const int dev0 = g_devices[0];
-    CU(cudaSetDevice(dev0));
-    LaneGuard lg;
-    if ((rc = lane_acquire(dev0, 256 + (size_t)D * 192 + 192 + 256, &lg.l))) return rc;
-    cudaStream_t s = lg.l->stream;
-    unsigned long long* d_status = reinterpret_cast<unsigned long long*>(lg.l->buf);
-    uint8_t* d_in = lg.l->buf + 256;
-    uint8_t* d_out = d_in + align_up((size_t)D * 192, 256);
-    for (int v = 0; v < 4; v++) {
-        const size_t usz = gs[v]->usize;
-        for (int half = 0; half < 2; half++) {
-            std::vector<uint8_t> stage((size_t)D * usz);
-            for (int di = 0; di < D; di++) memcpy(stage.data() + di * usz, partial[di].data() + op[v] + half * usz, usz);
-            CU(cudaMemsetAsync(d_status, 0xff, 8, s));
-            CU(cudaMemcpyAsync(d_in, stage.data(), stage.size(), cudaMemcpyHostToDevice, s));
-            gs[v]->sum_points(reinterpret_cast<const uint32_t*>(d_in), D, reinterpret_cast<uint32_t*>(d_out), d_status, s);
-            CU(cudaMemcpyAsync(pairs + op[v] + half * usz, d_out, usz, cudaMemcpyDeviceToHost, s));
-            unsigned long long st;
-            CU(cudaMemcpyAsync(&st, d_status, 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            if ((rc = decode_status(st, 0, "sum of partial ratio points"))) return rc;
-        }
-    }
-    return SS_OK;
+    std::vector<const uint8_t*> blobs(D);
+    for (int di = 0; di < D; di++) blobs[di] = partial[di].data();
+    return sum_pair_blobs(p->curve, blobs.data(), D, pairs);
 }
 
 int ss_phase1_verification_vectors(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
@@ -490,6 +527,43 @@ int ss_phase1_verification_vectors_dev(const ss_phase1_params* p, const void* d_
     return phase1_verification_impl(p, static_cast<const uint8_t*>(d_output), output_len, compressed_output,
                                     static_cast<uint8_t*>(d_new_challenge), new_challenge_len, compressed_new_challenge,
                                     subgroup_mode, ratio_check, rho_seed, pairs, false, static_cast<cudaStream_t>(stream));
+}
+
+// Index-range shard of the verification loop (see ss_phase1_computation_shard): `output` / `new_challenge` are the WHOLE
+// buffers, only the shard's ranges (plus one overlap element of the response for the ratio pairs) are touched, and
+// `pairs` receives the shard's PARTIAL (s, sx) — independent processes add theirs with ss_phase1_reduce_partial_pairs.
+int ss_phase1_verification_vectors_shard(const ss_phase1_params* p, const uint8_t* output, size_t output_len,
+                                         int compressed_output, uint8_t* new_challenge, size_t new_challenge_len,
+                                         int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                         const uint8_t* rho_seed, uint8_t* pairs, uint32_t shard_index, uint32_t shard_count) {
+    return phase1_verification_impl(p, output, output_len, compressed_output, new_challenge, new_challenge_len,
+                                    compressed_new_challenge, subgroup_mode, ratio_check, rho_seed, pairs, true, nullptr,
+                                    shard_index, shard_count);
+}
+
+int ss_phase1_verification_vectors_shard_dev(const ss_phase1_params* p, const void* d_output, size_t output_len,
+                                             int compressed_output, void* d_new_challenge, size_t new_challenge_len,
+                                             int compressed_new_challenge, int subgroup_mode, int ratio_check,
+                                             const uint8_t* rho_seed, uint8_t* pairs, uint32_t shard_index,
+                                             uint32_t shard_count, void* stream) {
+    return phase1_verification_impl(p, static_cast<const uint8_t*>(d_output), output_len, compressed_output,
+                                    static_cast<uint8_t*>(d_new_challenge), new_challenge_len, compressed_new_challenge,
+                                    subgroup_mode, ratio_check, rho_seed, pairs, false, static_cast<cudaStream_t>(stream),
+                                    shard_index, shard_count);
+}
+
+size_t ss_phase1_pairs_size(int curve) {
+    const GroupOps* g1 = group_ops(curve, SS_G1);
+    const GroupOps* g2 = group_ops(curve, SS_G2);
+    return (g1 && g2) ? 2 * (3 * (size_t)g1->usize + g2->usize) : 0;
+}
+
+int ss_phase1_reduce_partial_pairs(int curve, const uint8_t* partials, int count, uint8_t* pairs) {
+    const size_t blob_b = ss_phase1_pairs_size(curve);
+    if (!blob_b || !partials || count <= 0 || !pairs) return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "bad argument");
+    std::vector<const uint8_t*> blobs(count);
+    for (int k = 0; k < count; k++) blobs[k] = partials + (size_t)k * blob_b;
+    return sum_pair_blobs(curve, blobs.data(), count, pairs);
 }
 
 }  // extern "C"

@@ -290,12 +290,18 @@ SS_HD void endo_window(Jac<typename G::F>& acc, const typename G::F* tx, const t
 
 // ---- k * P ----------------------------------------------------------------------------------------
 // `k` canonical little-endian words (G::Fr::N of them), k < r.
+// PRECONDITION: `base` lies in the order-r subgroup (phi / psi act as the scalars lambda / u only there).  That is
+// what a ceremony's challenge holds — the coordinator verified it, which is why the reference's contribute reads it
+// with CheckForCorrectness::No (setup-utils/src/helpers.rs:550) — and what CHECK_FULL / CHECK_ONLY_IN_GROUP have
+// tested.  `plain` = true selects the reference's own MSB-first double-and-add instead (ss_set_strict_unchecked_inputs),
+// which reproduces ark-ec's mul_bigint on ANY input, off-subgroup or off-curve (the a = 0 formulas do not involve b).
 template <class G>
-SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, const uint32_t* k) {
+SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, const uint32_t* k, bool plain = false) {
     using F = typename G::F;
     using E = Endo<G>;
     constexpr int ND = E::ND, DIMS = E::DIMS, TS = 8;
     if (base.inf) return Jac<F>::identity();
+    if (plain) return jac_mul_ladder_cold<G>(base, k);
     // table j*P, j = 1..8, Jacobian
     F tx[TS], ty[TS], tz[TS];
     {

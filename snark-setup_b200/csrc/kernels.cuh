@@ -260,6 +260,7 @@ struct ScalarMulArgs {
     // fft_compact: the stage skips the butterflies whose twiddle is 1 (j = 0 of every block but block 0, whose
     // twiddle carries the 1/n): thread 0 is (block 0, j 0), thread t >= 1 is block (t-1)/(m-1), j = 1 + (t-1)%(m-1).
     int fft_compact = 0;
+    int plain_ladder = 0;  // 1: the reference's double-and-add for inputs that were not subgroup-checked (glv.cuh)
 };
 
 // bases[i] <- (exps[i] * coeff?) * bases[i]   (setup-utils/src/helpers.rs:95-106), result left in
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
 #if defined(SS_SCALAR_MUL_LADDER)
     Jac<F> r = jac_mul_bits<F>(base, [&](int k) { return s.l[k]; }, FrP::BITS);  // reference algorithm (A/B)
 #else
-    Jac<F> r = scalar_mul_endo<G>(base, s.l);  // GLV / GLS + signed windows + common-Z table (glv.cuh)
+    Jac<F> r = scalar_mul_endo<G>(base, s.l, a.plain_ladder != 0);  // GLV / GLS + signed windows + common-Z table (glv.cuh)
 #endif
     uint32_t* o = a.jac + i;
     FW::store(o, a.n, r.X);
@@ -408,14 +409,30 @@ struct SubgroupArgs {
     uint64_t n;  // SoA stride of `aff`
     unsigned long long* status;
     uint64_t count;  // elements to check (<= n)
+    // 1: the elements were read UNCOMPRESSED without validation, so they need not be on the curve.  The endomorphism
+    // tests equal r*P == O only on curve points; the reference runs r*P on whatever it was given
+    // (accumulator.rs:120-137), so an off-curve element falls back to that very multiplication (same b-free
+    // formulas => same verdict).
+    int maybe_off_curve = 0;
 };
+
+template <class G>
+#if defined(__CUDACC__)
+__device__ __noinline__
+#endif
+bool in_subgroup_rmul_cold(Affine<typename G::F> p) {
+    return in_subgroup_rmul<G>(p);
+}
 
 template <class G>
 __global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_SUBGROUP_MINB_NARROW)) k_subgroup(SubgroupArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.count) return;
     Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
-    if (!in_subgroup<G>(p)) report(a.status, i, ERR_INCORRECT_SUBGROUP);
+    bool ok;
+    if (a.maybe_off_curve && !on_curve(p, G::b())) ok = in_subgroup_rmul_cold<G>(p);
+    else ok = in_subgroup<G>(p);
+    if (!ok) report(a.status, i, ERR_INCORRECT_SUBGROUP);
 }
 
 // ---- sum of a few uncompressed points (adds the per-device partial (s, sx) of a sharded ratio check) ----

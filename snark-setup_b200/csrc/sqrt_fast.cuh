@@ -134,7 +134,9 @@ SS_HD bool fp_sqrt_fast(const FqB& a, FqB& out) {
     if (!sqrt_parts(a, w, x, e)) return false;
     if (e & 1) return false;
     out = fp_mul(x, sqrt_zeta_neg_half(e));
-    return true;
+    // the root comes out of lookup tables: one squaring proves it (a corrupted table entry or a hash collision
+    // must surface as "no root", never as an off-curve point that CheckForCorrectness::No would let through)
+    return fp_sqr(out) == a;
 }
 
 SS_HD bool fp2_sqrt_fast(const Fp2<Bls377Fq>& a, Fp2<Bls377Fq>& out) {
@@ -174,7 +176,7 @@ SS_HD bool fp2_sqrt_fast(const Fp2<Bls377Fq>& a, Fp2<Bls377Fq>& out) {
         FqB dinv = fp_mul(fp_mul(fp_sqr(w), fp_sqr(h)), sqrt_tab(kSqrtM5B, 0));    // 1/delta
         out = F2{fp_mul(a1h, fp_mul(s, dinv)), fp_neg(fp_mul(s, sqrt_tab(kSqrtInv5, 0)))};
     }
-    return true;
+    return fp_sqr(out) == a;  // see fp_sqrt_fast
 }
 
 // dispatch used by the codec: table-driven for BLS12-377, windowed power for p = 3 mod 4

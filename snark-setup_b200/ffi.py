@@ -317,47 +317,70 @@ def check_and_ratio(curve, group, inp, in_compressed, subgroup_mode=SUBGROUP_AUT
     return (bytes(out) if out is not None else None), s.raw, sx.raw
 
 
-def phase1_verification_vectors(params, output, compressed_output, new_challenge, compressed_new_challenge,
-                                subgroup_mode=SUBGROUP_AUTO, ratio_check=True, seed=None):
-    """Hot loop of Phase1::verification (phase1/src/verification.rs:217-411).  `new_challenge` is a
-    bytearray written in place (or None).  Returns [(s, sx)] for tau_g1, tau_g2, alpha_g1, beta_g1."""
-    cv = params.curve
-    u1, u2 = element_size(cv, G1, False), element_size(cv, G2, False)
-    pairs = C.create_string_buffer(2 * (3 * u1 + u2))
-    pin, k1 = _buf(output)
-    pnc, k2 = _buf(new_challenge) if new_challenge is not None else (None, None)
-    f = lib().ss_phase1_verification_vectors
-    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
-                  C.c_char_p, C.c_void_p]
-    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
-                  C.c_int, C.c_char_p, C.c_void_p]
-    _check(f(C.byref(params.c), pin, len(output), int(compressed_output), pnc,
-             len(new_challenge) if new_challenge is not None else 0, int(compressed_new_challenge), subgroup_mode,
-             int(ratio_check), bytes(seed) if seed is not None else None, pairs))
+def _split_pairs(curve, raw):
+    u1, u2 = element_size(curve, G1, False), element_size(curve, G2, False)
     out, o = [], 0
     for usz in (u1, u2, u1, u1):
-        out.append((pairs.raw[o:o + usz], pairs.raw[o + usz:o + 2 * usz]))
+        out.append((raw[o:o + usz], raw[o + usz:o + 2 * usz]))
         o += 2 * usz
     return out
+
+
+def pairs_size(curve):
+    f = lib().ss_phase1_pairs_size
+    f.restype = C.c_size_t
+    return f(curve)
+
+
+def phase1_verification_vectors(params, output, compressed_output, new_challenge, compressed_new_challenge,
+                                subgroup_mode=SUBGROUP_AUTO, ratio_check=True, seed=None, shard=None, raw=False):
+    """Hot loop of Phase1::verification (phase1/src/verification.rs:217-411).  `new_challenge` is a
+    bytearray written in place (or None).  Returns [(s, sx)] for tau_g1, tau_g2, alpha_g1, beta_g1.
+    shard=(index, count): only that index-range shard of every vector (partial sums; raw=True returns the blob
+    ss_phase1_reduce_partial_pairs takes)."""
+    cv = params.curve
+    pairs = C.create_string_buffer(pairs_size(cv))
+    pin, k1 = _buf(output)
+    pnc, k2 = _buf(new_challenge) if new_challenge is not None else (None, None)
+    si, sc = shard if shard is not None else (0, 1)
+    f = lib().ss_phase1_verification_vectors_shard
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                  C.c_int, C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    _check(f(C.byref(params.c), pin, len(output), int(compressed_output), pnc,
+             len(new_challenge) if new_challenge is not None else 0, int(compressed_new_challenge), subgroup_mode,
+             int(ratio_check), bytes(seed) if seed is not None else None, pairs, si, sc))
+    return pairs.raw if raw else _split_pairs(cv, pairs.raw)
 
 
 def phase1_verification_vectors_dev(params, d_output, output_len, compressed_output, d_new_challenge, nc_len,
                                     compressed_new_challenge, subgroup_mode=SUBGROUP_AUTO, ratio_check=True, seed=None,
-                                    stream=0):
+                                    stream=0, shard=None, raw=False):
     cv = params.curve
-    u1, u2 = element_size(cv, G1, False), element_size(cv, G2, False)
-    pairs = C.create_string_buffer(2 * (3 * u1 + u2))
-    f = lib().ss_phase1_verification_vectors_dev
+    pairs = C.create_string_buffer(pairs_size(cv))
+    si, sc = shard if shard is not None else (0, 1)
+    f = lib().ss_phase1_verification_vectors_shard_dev
     f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
-                  C.c_int, C.c_char_p, C.c_void_p, C.c_void_p]
+                  C.c_int, C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     _check(f(C.byref(params.c), d_output, output_len, int(compressed_output), d_new_challenge, nc_len,
              int(compressed_new_challenge), subgroup_mode, int(ratio_check), bytes(seed) if seed is not None else None,
-             pairs, stream))
-    out, o = [], 0
-    for usz in (u1, u2, u1, u1):
-        out.append((pairs.raw[o:o + usz], pairs.raw[o + usz:o + 2 * usz]))
-        o += 2 * usz
-    return out
+             pairs, si, sc, stream))
+    return pairs.raw if raw else _split_pairs(cv, pairs.raw)
+
+
+def phase1_reduce_partial_pairs(curve, blobs, raw=False):
+    """Host-side reduction of the shards' partial (s, sx): element-wise group sums of the blobs."""
+    n = pairs_size(curve)
+    blobs = [bytes(b) for b in blobs]
+    assert all(len(b) == n for b in blobs)
+    out = C.create_string_buffer(n)
+    f = lib().ss_phase1_reduce_partial_pairs
+    f.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_void_p]
+    _check(f(curve, b"".join(blobs), len(blobs), out))
+    return out.raw if raw else _split_pairs(curve, out.raw)
+
+
+def set_strict_unchecked_inputs(on=True):
+    lib().ss_set_strict_unchecked_inputs(1 if on else 0)
 
 
 class Phase1Parameters:
@@ -499,6 +522,13 @@ def check_same_ratio_batch(curve, g1_pairs, g2_pairs):
     _check(f(curve, bytes(g1_pairs), bytes(g2_pairs), n, C.byref(bad)))
 
 
+def phase1_check_ratio_pairs(curve, pairs, g1_check, g2_check):
+    """The four check_same_ratio of a response from its (reduced) `pairs` blob; raises InvalidRatio (.index = vector)."""
+    f = lib().ss_phase1_check_ratio_pairs
+    f.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
+    _check(f(curve, bytes(pairs), bytes(g1_check), bytes(g2_check)))
+
+
 def phase1_verification_ratios(params, output, compressed_output, new_challenge, compressed_new_challenge,
                                check_output=CHECK_FULL, subgroup_mode=SUBGROUP_AUTO, seed=None):
     """Per-vector half of Phase1::verification with its verdict (phase1/src/verification.rs:44-80,217-411):
@@ -541,20 +571,27 @@ def qap_dot_product(curve, group, bases, bases_compressed, rows, out_compressed,
 
 
 def phase1_computation(params: Phase1Parameters, inp, out, compressed_input, compressed_output, check_input,
-                       tau, alpha, beta):
-    """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place."""
+                       tau, alpha, beta, shard=None):
+    """Phase1::computation (phase1/src/computation.rs:16-308) on host buffers; `out` is written in place.
+    shard=(index, count): only that index-range shard of every vector is read and written."""
     pin, k1 = _buf(inp)
     pout, k2 = _buf(out)
     cv = params.curve
-    _check(lib().ss_phase1_computation(C.byref(params.c), pin, len(inp), pout, len(out), int(compressed_input),
-                                       int(compressed_output), check_input, _scalar(cv, tau), _scalar(cv, alpha),
-                                       _scalar(cv, beta)))
+    si, sc = shard if shard is not None else (0, 1)
+    f = lib().ss_phase1_computation_shard
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                  C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32]
+    _check(f(C.byref(params.c), pin, len(inp), pout, len(out), int(compressed_input), int(compressed_output),
+             check_input, _scalar(cv, tau), _scalar(cv, alpha), _scalar(cv, beta), si, sc))
 
 
 def phase1_computation_dev(params: Phase1Parameters, d_in, in_len, d_out, out_len, compressed_input,
-                           compressed_output, check_input, tau, alpha, beta, stream=0):
+                           compressed_output, check_input, tau, alpha, beta, stream=0, shard=None):
     """Same, on device pointers (ints) of the current CUDA device."""
     cv = params.curve
-    _check(lib().ss_phase1_computation_dev(C.byref(params.c), d_in, in_len, d_out, out_len, int(compressed_input),
-                                           int(compressed_output), check_input, _scalar(cv, tau), _scalar(cv, alpha),
-                                           _scalar(cv, beta), stream))
+    si, sc = shard if shard is not None else (0, 1)
+    f = lib().ss_phase1_computation_shard_dev
+    f.argtypes = [C.POINTER(_P1Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                  C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    _check(f(C.byref(params.c), d_in, in_len, d_out, out_len, int(compressed_input), int(compressed_output),
+             check_input, _scalar(cv, tau), _scalar(cv, alpha), _scalar(cv, beta), si, sc, stream))

@@ -18,12 +18,31 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def ratio_shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
-    """Element range a rank must READ to produce its partial power_pairs: its pairs (i, i+1) for i in
-    shard_range(n-1), i.e. one element of overlap with the next shard.  Empty when it owns no pair."""
-    if n < 2:
-        return 0, 0
-    s, e = shard_range(n - 1, rank, world)
-    return (s, e + 1) if e > s else (s, s)
+    """Element range a rank must READ for its partial power_pairs (api_ratio.inl does the same arithmetic): its own
+    elements shard_range(n) plus ONE element of overlap with the next shard, because the pair (i, i+1) belongs to the
+    owner of element i.  The last non-empty shard reads no overlap; a shard that ends up with one element and no
+    successor owns no pair."""
+    s, e = shard_range(n, rank, world)
+    if e == s:
+        return s, s
+    return (s, e + 1) if e < n else (s, e)
+
+
+def vector_offsets(g1_count: int, other_count: int, compressed: bool, g1_sizes=(96, 48), g2_sizes=(192, 96)):
+    """[(byte offset, element count, element size)] of tau_g1, tau_g2, alpha_g1, beta_g1, beta_g2 in a Groth16
+    accumulator buffer (phase1/src/helpers/buffers.rs:293-341); sizes default to BLS12-377 (uncompressed, compressed)."""
+    s1, s2 = g1_sizes[1 if compressed else 0], g2_sizes[1 if compressed else 0]
+    out, off = [], 64
+    for cnt, sz in ((g1_count, s1), (other_count, s2), (other_count, s1), (other_count, s1), (1, s2)):
+        out.append((off, cnt, sz))
+        off += cnt * sz
+    return out
+
+
+def shard_bytes(n: int, rank: int, world: int, element_size: int) -> int:
+    """Bytes of one vector that belong to `rank`'s shard."""
+    s, e = shard_range(n, rank, world)
+    return (e - s) * element_size
 
 
 def contribute_plan(g1_count: int, other_count: int, first_power: int, rank: int, world: int):
