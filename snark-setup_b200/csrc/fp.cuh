@@ -230,6 +230,98 @@ SS_HD Fp<P> fp_mul_inl(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// ---- sum of two products ----------------------------------------------------------------------------
+// (a*b + c*d) / R mod p with ONE interleaved reduction: 2 N^2 products + N^2 reduction instead of the 4 N^2 of two
+// multiplications.  Used by the lane-split Fq2 arithmetic (fp2l.cuh), where one lane computes a0 b0 + a1 (-5 b1) and
+// the other a0 b1 + a1 b0.  Operand bounds: a, c < 2p and b, d < 2^(32 N) with a*b + c*d < p*R (callers keep
+// b, d <= 5p, i.e. a*b + c*d <= 20 p^2 < p*R since R/p > 2^7); every partial sum then fits the N+1 limbs of (X, Y):
+// T + a*b_i + c*d_i + m*p < 2^32 (2p + 2p + p) + 2p, far below 2^(32 (N+1)).  The result is < 1.2 p before the final
+// conditional subtraction.
+// accumulate one more product row c * di into (X, Y) WITHOUT shifting (same shape as mont_reduce_step with p := c)
+template <class P>
+SS_HD void mont_row_acc(uint32_t* X, uint32_t* Y, const uint32_t* c, uint32_t di) {
+    constexpr int N = P::N;
+    Y[0] = mad_lo_cc(c[1], di, Y[0]);
+    Y[1] = madc_hi_cc(c[1], di, Y[1]);
+#pragma unroll
+    for (int j = 2; j < N - 2; j += 2) {
+        Y[j] = madc_lo_cc(c[j + 1], di, Y[j]);
+        Y[j + 1] = madc_hi_cc(c[j + 1], di, Y[j + 1]);
+    }
+    Y[N - 2] = madc_lo_cc(c[N - 1], di, Y[N - 2]);
+    Y[N - 1] = madc_hi(c[N - 1], di, Y[N - 1]);
+    X[0] = mad_lo_cc(c[0], di, X[0]);
+    X[1] = madc_hi_cc(c[0], di, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(c[j], di, X[j]);
+        X[j + 1] = madc_hi_cc(c[j], di, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0);
+}
+
+// the shifting product row of mont_step without its reduction
+template <class P>
+SS_HD void mont_row_shift(uint32_t* X /*old Y*/, uint32_t* Y /*old X*/, const uint32_t* a, uint32_t bi) {
+    constexpr int N = P::N;
+    X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        Y[j] = madc_lo_cc(a[j + 1], bi, Y[j + 2]);
+        Y[j + 1] = madc_hi_cc(a[j + 1], bi, Y[j + 3]);
+    }
+    Y[N - 2] = madc_lo_cc(a[N - 1], bi, 0);
+    Y[N - 1] = madc_hi(a[N - 1], bi, 0);
+    X[0] = mad_lo_cc(a[0], bi, X[0]);
+    X[1] = madc_hi_cc(a[0], bi, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        X[j] = madc_lo_cc(a[j], bi, X[j]);
+        X[j + 1] = madc_hi_cc(a[j], bi, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0);
+}
+
+template <class P>
+SS_HD Fp<P> fp_mul2_inl(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    constexpr int N = P::N;
+    uint32_t X[N], Y[N];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        X[j] = mul_lo(a.l[j], b.l[0]);
+        X[j + 1] = mul_hi(a.l[j], b.l[0]);
+        Y[j] = mul_lo(a.l[j + 1], b.l[0]);
+        Y[j + 1] = mul_hi(a.l[j + 1], b.l[0]);
+    }
+    mont_row_acc<P>(X, Y, c.l, d.l[0]);
+    mont_reduce_step<P>(X, Y);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_row_shift<P>(Y, X, a.l, b.l[i]);
+        mont_row_acc<P>(Y, X, c.l, d.l[i]);
+        mont_reduce_step<P>(Y, X);
+        if (i + 1 < N) {
+            mont_row_shift<P>(X, Y, a.l, b.l[i + 1]);
+            mont_row_acc<P>(X, Y, c.l, d.l[i + 1]);
+            mont_reduce_step<P>(X, Y);
+        }
+    }
+    Fp<P> r;
+    r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(X[j], Y[j + 1]);
+    r.l[N - 1] = addc(X[N - 1], 0);
+    fp_final_sub<P>(r.l);
+    return r;
+}
+
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Fp<P> fp_mul2_call(Fp<P> a, Fp<P> b, Fp<P> c, Fp<P> d) {
+    return fp_mul2_inl(a, b, c, d);
+}
+#endif
+
 // ---- dedicated squaring --------------------------------------------------------------------------
 // a^2 = 2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum_i a_i^2 2^(64 i): N(N+1)/2 wide products instead of N^2,
 // followed by a separate Montgomery reduction of the 2N-limb square (N^2 wide products): 222 instead
@@ -312,7 +404,7 @@ __device__ __noinline__ Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) {
 // ss_op_count[0][N] multiplications, [1][N] squarings on N-limb fields.  bench.py's "executed work" figure is
 // pinned by tests/test_device_algos_emul.py::test_executed_work_per_scalar_mul with these counters.
 #if defined(SS_COUNT_OPS) && !defined(__CUDACC__)
-inline unsigned long long ss_op_count[2][32] = {};
+inline unsigned long long ss_op_count[3][32] = {};
 #define SS_COUNT_OP(kind, n) (++ss_op_count[kind][n])
 #else
 #define SS_COUNT_OP(kind, n) ((void)0)
@@ -325,6 +417,17 @@ SS_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #else
     SS_COUNT_OP(0, P::N);
     return fp_mul_inl(a, b);
+#endif
+}
+
+template <class P>
+SS_HD Fp<P> fp_mul2(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+#if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+    return fp_mul2_call<P>(a, b, c, d);
+#else
+    SS_COUNT_OP(0, P::N);
+    SS_COUNT_OP(2, P::N);  // [2][N]: how many of the counted multiplications were the 1.5x sum-of-two-products form
+    return fp_mul2_inl(a, b, c, d);
 #endif
 }
 
