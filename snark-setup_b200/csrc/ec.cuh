@@ -9,6 +9,7 @@
 #pragma once
 #include "constants_gen.cuh"
 #include "fp2.cuh"
+#include "fp2l.cuh"
 
 namespace ss {
 
@@ -81,6 +82,39 @@ struct Bls377G2 {
         return g;
     }
 };
+
+#if defined(__CUDACC__)
+// Lane-split twin of Bls377G2 (fp2l.cuh): the same group, one element per LANE PAIR.  Only the kernels whose time is
+// group arithmetic use it (scalar multiplication, subgroup test, bucket accumulation); serialisation, normalisation
+// and the reductions keep the per-thread form and the two share every HBM layout.
+struct Bls377G2L {
+    using F = Fp2L<Bls377Fq>;
+    using Fr = Fp<Bls377Fr>;
+    using GP = Bls377G2Params;
+    using Wide = Bls377G2;
+    static constexpr int USIZE = 192, CSIZE = 96;
+#ifndef SS_G2L_MINB
+#define SS_G2L_MINB 3
+#endif
+    static constexpr int SMUL_MINB = SS_G2L_MINB;  // 128-thread blocks per SM (168 registers at 3)
+    static const char* name() { return "bls12_377.g2"; }
+    SS_HD static F b() {
+        F r;
+        const int odd = lane_odd();
+#pragma unroll
+        for (int i = 0; i < 12; i++) r.h.l[i] = odd ? GP::b_c1(i) : GP::b_c0(i);
+        return r;
+    }
+};
+template <class G>
+struct PairTwin {
+    using type = void;
+};
+template <>
+struct PairTwin<Bls377G2> {
+    using type = Bls377G2L;
+};
+#endif
 
 template <class GPx>
 struct Bw6Group {
@@ -234,6 +268,132 @@ SS_HD Jac<F> jac_add(const Jac<F>& p, const Jac<F>& q) {
 #endif
     return jac_add_inl(p, q);
 }
+
+#if defined(__CUDACC__)
+// ---- group law on lane-split elements (fp2l.cuh): converged-warp versions ---------------------------------------
+// Same formulas; the exceptional cases are resolved by SELECTION after the common computation, and the one that needs
+// more arithmetic (P + P) is entered by the whole warp behind __any_sync, so that every lane executes the same
+// sequence of exchanges.  More specialised than the generic templates above, so overload resolution picks them for
+// Jac<Fp2L<P>> wherever the generic code calls jac_dbl / jac_madd / jac_add (or their _inl / _cold forms).
+template <class P>
+SS_D Fp2L<P> f2l_select(bool c, const Fp2L<P>& a, const Fp2L<P>& b) {
+    Fp2L<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.h.l[i] = c ? a.h.l[i] : b.h.l[i];
+    return r;
+}
+template <class P>
+SS_D Jac<Fp2L<P>> jac_select(bool c, const Jac<Fp2L<P>>& a, const Jac<Fp2L<P>>& b) {
+    return Jac<Fp2L<P>>{f2l_select(c, a.X, b.X), f2l_select(c, a.Y, b.Y), f2l_select(c, a.Z, b.Z)};
+}
+
+// dbl-2009-l needs no case distinction: Z = 0 (or Y = 0) gives Z3 = 2 Y Z = 0, i.e. the identity
+template <class P>
+SS_D Jac<Fp2L<P>> jac_dbl_inl(const Jac<Fp2L<P>>& p) {
+    using F = Fp2L<P>;
+    F A = fp_sqr(p.X);
+    F B = fp_sqr(p.Y);
+    F C = fp_sqr(B);
+    F t = fp_sqr(fp_add(p.X, B));
+    F D = fp_dbl(fp_sub(fp_sub(t, A), C));
+    F E = fp_add(fp_dbl(A), A);
+    F Fq = fp_sqr(E);
+    Jac<F> r;
+    r.X = fp_sub(Fq, fp_dbl(D));
+    F C8 = fp_dbl(fp_dbl(fp_dbl(C)));
+    r.Z = fp_dbl(fp_mul(p.Y, p.Z));
+    r.Y = fp_sub(fp_mul(E, fp_sub(D, r.X)), C8);
+    return r;
+}
+template <class P>
+SS_D Jac<Fp2L<P>> jac_dbl_cold(const Jac<Fp2L<P>>& p) { return jac_dbl_inl(p); }
+template <class P>
+SS_D Jac<Fp2L<P>> jac_dbl(const Jac<Fp2L<P>>& p) { return jac_dbl_inl(p); }
+
+template <class P>
+SS_D Jac<Fp2L<P>> jac_madd_inl(const Jac<Fp2L<P>>& p, const Affine<Fp2L<P>>& q) {
+    using F = Fp2L<P>;
+    F Z1Z1 = fp_sqr(p.Z);
+    F U2 = fp_mul(q.x, Z1Z1);
+    F S2 = fp_mul(fp_mul(q.y, p.Z), Z1Z1);
+    F H = fp_sub(U2, p.X);
+    F rr = fp_sub(S2, p.Y);
+    const bool pinf = p.Z.is_zero(), hz = H.is_zero(), rz = rr.is_zero();
+    const bool exc = !q.inf && !pinf && hz;  // P = +-Q
+    rr = fp_dbl(rr);
+    F HH = fp_sqr(H);
+    F I = fp_dbl(fp_dbl(HH));
+    F J = fp_mul(H, I);
+    F V = fp_mul(p.X, I);
+    Jac<F> r;
+    r.X = fp_sub(fp_sub(fp_sqr(rr), J), fp_dbl(V));
+    r.Y = fp_sub(fp_mul(rr, fp_sub(V, r.X)), fp_dbl(fp_mul(p.Y, J)));
+    r.Z = fp_sub(fp_sub(fp_sqr(fp_add(p.Z, H)), Z1Z1), HH);
+    if (warp_any(exc && rz)) r = jac_select(exc && rz, jac_dbl_inl(p), r);
+    r = jac_select(exc && !rz, Jac<F>::identity(), r);
+    r = jac_select(pinf, Jac<F>{q.x, q.y, F::one()}, r);
+    return jac_select(q.inf, p, r);
+}
+template <class P>
+SS_D Jac<Fp2L<P>> jac_madd(const Jac<Fp2L<P>>& p, const Affine<Fp2L<P>>& q) { return jac_madd_inl(p, q); }
+
+template <class P>
+SS_D Jac<Fp2L<P>> jac_add_inl(const Jac<Fp2L<P>>& p, const Jac<Fp2L<P>>& q) {
+    using F = Fp2L<P>;
+    F Z1Z1 = fp_sqr(p.Z);
+    F Z2Z2 = fp_sqr(q.Z);
+    F U1 = fp_mul(p.X, Z2Z2);
+    F U2 = fp_mul(q.X, Z1Z1);
+    F S1 = fp_mul(fp_mul(p.Y, q.Z), Z2Z2);
+    F S2 = fp_mul(fp_mul(q.Y, p.Z), Z1Z1);
+    F H = fp_sub(U2, U1);
+    F rr = fp_sub(S2, S1);
+    const bool pinf = p.Z.is_zero(), qinf = q.Z.is_zero(), hz = H.is_zero(), rz = rr.is_zero();
+    const bool exc = !pinf && !qinf && hz;
+    rr = fp_dbl(rr);
+    F I = fp_sqr(fp_dbl(H));
+    F J = fp_mul(H, I);
+    F V = fp_mul(U1, I);
+    Jac<F> r;
+    r.X = fp_sub(fp_sub(fp_sqr(rr), J), fp_dbl(V));
+    r.Y = fp_sub(fp_mul(rr, fp_sub(V, r.X)), fp_dbl(fp_mul(S1, J)));
+    r.Z = fp_mul(fp_sub(fp_sub(fp_sqr(fp_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
+    if (warp_any(exc && rz)) r = jac_select(exc && rz, jac_dbl_inl(p), r);
+    r = jac_select(exc && !rz, Jac<F>::identity(), r);
+    r = jac_select(qinf, p, r);
+    return jac_select(pinf, q, r);
+}
+template <class P>
+SS_D Jac<Fp2L<P>> jac_add(const Jac<Fp2L<P>>& p, const Jac<Fp2L<P>>& q) { return jac_add_inl(p, q); }
+
+// MSB-first double-and-add with the addition computed by every lane and SELECTED by the bit (per-lane scalars must not
+// diverge the warp); `base.inf` is resolved at the end.  The slow paths only: strict mode, tiny-order bases, r * P.
+template <class P, class LimbFn>
+SS_D Jac<Fp2L<P>> jac_mul_bits_pair(const Affine<Fp2L<P>>& base, LimbFn limb, int nbits) {
+    using F = Fp2L<P>;
+    Affine<F> b = base;
+    b.inf = false;
+    Jac<F> acc = Jac<F>::identity();
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        acc = jac_dbl_inl(acc);
+        const bool bit = ((limb(i >> 5) >> (i & 31)) & 1) != 0;
+        acc = jac_select(bit, jac_madd_inl(acc, b), acc);
+    }
+    return jac_select(base.inf, Jac<F>::identity(), acc);
+}
+
+// Jacobian J == affine (ax, ay), all comparisons evaluated by every lane
+template <class P>
+SS_D bool jac_eq_affine_pair(const Jac<Fp2L<P>>& j, const Fp2L<P>& ax, const Fp2L<P>& ay) {
+    using F = Fp2L<P>;
+    const bool zz = j.Z.is_zero();
+    F z2 = fp_sqr(j.Z);
+    const bool ex = j.X == fp_mul(ax, z2);
+    const bool ey = j.Y == fp_mul(ay, fp_mul(z2, j.Z));
+    return !zz && ex && ey;
+}
+#endif  // __CUDACC__
 
 template <class F>
 SS_HD Affine<F> affine_neg(const Affine<F>& p) {

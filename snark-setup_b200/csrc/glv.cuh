@@ -228,6 +228,35 @@ struct Endo<Bls377G2> {
     }
 };
 
+#if defined(__CUDACC__)
+// the same endomorphism on the lane-split representation: every map is per-lane (a base-field multiplication of the
+// own half, a sign on the odd lane), no exchange needed
+template <>
+struct Endo<Bls377G2L> {
+    using B = Fp<Bls377Fq>;
+    using F = Fp2L<Bls377Fq>;
+    using P = Bls377G2Gls;
+    static constexpr int DIMS = 4, ND = P::ND;
+    SS_HD static void decompose(const uint32_t* k, int8_t* dig) { gls4_decompose<P>(k, dig); }
+    SS_HD static void apply(int j, F& x, F& y) {
+        if (j == 1) {
+            x = fp_conj(fp_mul_base(x, Endo<Bls377G2>::cst(0)));
+            y = fp_conj(fp_mul_base(y, Endo<Bls377G2>::cst(1)));
+        } else if (j == 2) {
+            x = fp_mul_base(x, Endo<Bls377G2>::cst(2));
+            y = fp_neg(y);
+        } else if (j == 3) {
+            x = fp_conj(fp_neg(x));
+            y = fp_neg(fp_conj(fp_mul_base(y, Endo<Bls377G2>::cst(1))));
+        }
+    }
+    SS_HD static bool real_factor(const F& zc, F& out) {
+        out = fp_conj(zc);
+        return true;
+    }
+};
+#endif
+
 // out-of-line plain ladder for the (never taken on subgroup inputs) tiny-order fallback
 template <class G>
 #if defined(__CUDACC__)
@@ -348,5 +377,89 @@ SS_HD Jac<typename G::F> scalar_mul_endo(const Affine<typename G::F>& base, cons
     acc.Z = fp_mul(acc.Z, zfinal);
     return acc;
 }
+
+
+#if defined(__CUDACC__)
+// ---- k * P on the lane-split group: scalar_mul_endo under the converged-warp discipline of fp2l.cuh -----------------
+// Same algorithm (common-Z table of {1..8} P, 4-dim GLS digits, signed 4-bit windows); what changes is control flow:
+// a zero digit adds a dummy entry and keeps the old accumulator by selection, an infinite base runs on a harmless
+// stand-in and is resolved at the end, and the tiny-order fallback (some j P = O) is entered by the whole warp.
+template <class GL>
+SS_D Jac<typename GL::F> scalar_mul_endo_pair(const Affine<typename GL::F>& base_in, const uint32_t* k, bool plain) {
+    using F = typename GL::F;
+    using E = Endo<GL>;
+    using FrP = typename GL::Fr::Params;
+    constexpr int ND = E::ND, DIMS = E::DIMS, TS = 8;
+    Affine<F> base = base_in;
+    if (plain)  // kernel argument: uniform
+        return jac_mul_bits_pair<typename F::Params>(base, [&](int i) { return k[i]; }, FrP::BITS);
+    base.inf = false;
+    // an infinite base carries x = y = 0: the table arithmetic below runs on it without harm (Z products become 0,
+    // which would request the ladder) — its result is replaced by the identity at the end and it never votes
+    F tx[TS], ty[TS], tz[TS];
+    {
+        Jac<F> t{base.x, base.y, F::one()};
+        tx[0] = t.X; ty[0] = t.Y; tz[0] = t.Z;
+        t = jac_dbl_inl(t);
+        tx[1] = t.X; ty[1] = t.Y; tz[1] = t.Z;
+#pragma unroll 1
+        for (int j = 2; j < TS; j++) {
+            t = jac_madd_inl(t, base);
+            tx[j] = t.X; ty[j] = t.Y; tz[j] = t.Z;
+        }
+    }
+    F pre[TS];
+    pre[1] = F::one();
+#pragma unroll 1
+    for (int j = 2; j < TS; j++) pre[j] = fp_mul(pre[j - 1], tz[j - 1]);
+    F zc = fp_mul(pre[TS - 1], tz[TS - 1]);
+    const bool need_ladder = !base_in.inf && zc.is_zero();
+    F extra;
+    E::real_factor(zc, extra);
+    F zfinal = fp_mul(zc, extra);
+    {
+        F suf = extra;
+#pragma unroll 1
+        for (int j = TS - 1; j >= 1; j--) {
+            F f = fp_mul(pre[j], suf);
+            suf = fp_mul(suf, tz[j]);
+            F f2 = fp_sqr(f);
+            tx[j] = fp_mul(tx[j], f2);
+            ty[j] = fp_mul(ty[j], fp_mul(f2, f));
+        }
+        F f2 = fp_sqr(suf);
+        tx[0] = fp_mul(tx[0], f2);
+        ty[0] = fp_mul(ty[0], fp_mul(f2, suf));
+    }
+    int8_t dig[DIMS * ND];
+    E::decompose(k, dig);
+    Jac<F> acc = Jac<F>::identity();
+#pragma unroll 1
+    for (int i = ND - 1; i >= 0; i--) {
+        if (i != ND - 1) {
+#pragma unroll 1
+            for (int d = 0; d < 4; d++) acc = jac_dbl_inl(acc);
+        }
+#pragma unroll 1
+        for (int j = 0; j < DIMS; j++) {
+            const int d = dig[j * ND + i];
+            const int a = d < 0 ? -d : (d == 0 ? 1 : d);
+            Affine<F> q;
+            q.x = tx[a - 1];
+            q.y = ty[a - 1];
+            q.inf = false;
+            E::apply(j, q.x, q.y);
+            q.y = f2l_select(d < 0, fp_neg(q.y), q.y);
+            acc = jac_select(d != 0, jac_madd_inl(acc, q), acc);
+        }
+    }
+    acc.Z = fp_mul(acc.Z, zfinal);
+    if (warp_any(need_ladder)) {
+        Jac<F> lad = jac_mul_bits_pair<typename F::Params>(base, [&](int i) { return k[i]; }, FrP::BITS);
+        acc = jac_select(need_ladder, lad, acc);
+    }
+    return jac_select(base_in.inf, Jac<F>::identity(), acc);
+}
+#endif
 
 }  // namespace ss

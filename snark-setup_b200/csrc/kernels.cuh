@@ -13,6 +13,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "codec.cuh"
 #include "glv.cuh"
 
@@ -321,6 +324,82 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
     FW::store(o + (uint64_t)2 * FW::W * a.n, a.n, r.Z);
 }
 
+// ---- lane-split twins (fp2l.cuh): one element per LANE PAIR, the even lane owns the c0 halves, the odd lane c1 ------
+// Same HBM layouts as the per-thread kernels: the affine scratch [n][x.c0 | x.c1 | y.c0 | y.c1] is read as 48-byte
+// halves (three 16-byte loads per coordinate), the Jacobian SoA rows (c * FW + 12 * odd + k) are written by the lane
+// that owns them.
+template <class GL>
+SS_D Affine<typename GL::F> load_affine_half(const uint32_t* aff, const uint8_t* inf, uint64_t i) {
+    using F = typename GL::F;
+    constexpr int HW = F::Base::N;  // words per half coordinate
+    const int odd = lane_odd();
+    Affine<F> p;
+    const uint4* sx = reinterpret_cast<const uint4*>(aff + i * (4 * HW) + odd * HW);
+    const uint4* sy = reinterpret_cast<const uint4*>(aff + i * (4 * HW) + 2 * HW + odd * HW);
+#pragma unroll
+    for (int k = 0; k < HW / 4; k++) {
+        const uint4 a = sx[k], b = sy[k];
+        p.x.h.l[4 * k] = a.x; p.x.h.l[4 * k + 1] = a.y; p.x.h.l[4 * k + 2] = a.z; p.x.h.l[4 * k + 3] = a.w;
+        p.y.h.l[4 * k] = b.x; p.y.h.l[4 * k + 1] = b.y; p.y.h.l[4 * k + 2] = b.z; p.y.h.l[4 * k + 3] = b.w;
+    }
+    p.inf = inf[i] != 0;
+    return p;
+}
+
+template <class GL>
+__global__ void __launch_bounds__(SS_SMUL_TPB, GL::SMUL_MINB) k_scalar_mul_pair(ScalarMulArgs a) {
+    using F = typename GL::F;
+    using FrP = typename GL::Fr::Params;
+    constexpr int FRW = FrP::N, HW = F::Base::N, FW = 2 * HW;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = (t >> 1) < a.n;             // both lanes of a pair work on element i
+    const uint64_t i = live ? (t >> 1) : a.n - 1;  // out-of-range lanes stay in the warp on a clamped index (fp2l.cuh)
+    uint64_t src = i, pw = i & a.power_mask;
+    if (a.src_log_m >= 0) {
+        const uint64_t m = 1ull << a.src_log_m;
+        uint64_t blk = i >> a.src_log_m, j = i & (m - 1);
+        if (a.fft_compact) {
+            blk = i ? (i - 1) / (m - 1) : 0;
+            j = i ? 1 + (i - 1) % (m - 1) : 0;
+            pw = j;
+        }
+        src = (blk << (a.src_log_m + 1)) | m | j;
+    } else if (a.gather) {
+        src = a.gather[i];
+    }
+    Affine<F> base = load_affine_half<GL>(a.aff, a.inf, src);
+    Fp<FrP> s;  // both lanes derive the same scalar (a few Fr multiplications)
+    if (a.exps) {
+#pragma unroll
+        for (int k = 0; k < FRW; k++) s.l[k] = a.exps[i * FRW + k];
+        if (a.has_coeff) {
+            Fp<FrP> c;
+#pragma unroll
+            for (int k = 0; k < FRW; k++) c.l[k] = __ldg(a.coeff_m + k);
+            s = fp_mul(s, c);
+        }
+    } else {
+        s = tau_power<FrP>(a.tau_tab, a.first_power + pw);
+        if (a.has_coeff && i < a.coeff_limit) {
+            Fp<FrP> c;
+#pragma unroll
+            for (int k = 0; k < FRW; k++) c.l[k] = __ldg(a.coeff_m + k);
+            s = fp_mul(s, c);
+        }
+        s = fp_from_mont(s);
+    }
+    Jac<F> r = scalar_mul_endo_pair<GL>(base, s.l, a.plain_ladder != 0);
+    if (!live) return;
+    const int odd = lane_odd();
+    uint32_t* o = a.jac + i + (uint64_t)odd * HW * a.n;
+#pragma unroll
+    for (int k = 0; k < HW; k++) {
+        o[(uint64_t)k * a.n] = r.X.h.l[k];
+        o[(uint64_t)(FW + k) * a.n] = r.Y.h.l[k];
+        o[(uint64_t)(2 * FW + k) * a.n] = r.Z.h.l[k];
+    }
+}
+
 // ---- stage 3: normalize_batch + write_batch -----------------------------------------------------
 struct NormalizeArgs {
     const uint32_t* jac;  // [3*FW][n]
@@ -435,6 +514,49 @@ __global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_SUBGROUP_M
     if (!ok) report(a.status, i, ERR_INCORRECT_SUBGROUP);
 }
 
+// psi(P) == [u] P on the lane-split representation (codec.cuh in_subgroup_endo for Bls377G2), every lane of the warp
+// executing the same operations; an infinite element runs on its zero coordinates and is accepted at the end
+template <class GL>
+SS_D bool in_subgroup_pair(const Affine<typename GL::F>& p, bool maybe_off_curve) {
+    using F = typename GL::F;
+    using P = typename F::Params;
+    Affine<F> q = p;
+    q.inf = false;
+#if defined(SS_SUBGROUP_RMUL)
+    bool ok = jac_mul_bits_pair<P>(q, [](int i) { return GL::GP::order(i); }, GL::GP::ORDER_BITS).Z.is_zero();
+#else
+    Jac<F> acc{q.x, q.y, F::one()};
+#pragma unroll 1
+    for (int i = 62; i >= 0; i--) {  // [u] P, u = 0x8508c00000000001 (uniform bits)
+        acc = jac_dbl_inl(acc);
+        if ((kBls377U >> i) & 1) acc = jac_madd_inl(acc, q);
+    }
+    F x = q.x, y = q.y;
+    Endo<GL>::apply(1, x, y);
+    bool ok = jac_eq_affine_pair(acc, x, y);
+    // an element read uncompressed without validation may be off the curve: the reference then still runs r * P on its
+    // b-free formulas (accumulator.rs:120-137) — reproduce that verdict, warp-wide only when some lane needs it
+    if (maybe_off_curve) {
+        const bool off = !p.inf && !(fp_sqr(q.y) == fp_add(fp_mul(fp_sqr(q.x), q.x), GL::b()));
+        if (warp_any(off)) {
+            const bool rm = jac_mul_bits_pair<P>(q, [](int i) { return GL::GP::order(i); }, GL::GP::ORDER_BITS).Z.is_zero();
+            ok = off ? rm : ok;
+        }
+    }
+#endif
+    return p.inf || ok;
+}
+
+template <class GL>
+__global__ void __launch_bounds__(128, GL::SMUL_MINB) k_subgroup_pair(SubgroupArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = (t >> 1) < a.count;
+    const uint64_t i = live ? (t >> 1) : a.count - 1;
+    Affine<typename GL::F> p = load_affine_half<GL>(a.aff, a.inf, i);
+    const bool ok = in_subgroup_pair<GL>(p, a.maybe_off_curve != 0);
+    if (live && !ok && !lane_odd()) report(a.status, i, ERR_INCORRECT_SUBGROUP);
+}
+
 // ---- sum of a few uncompressed points (adds the per-device partial (s, sx) of a sharded ratio check) ----
 template <class G>
 __global__ void k_sum_points(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status) {
@@ -503,8 +625,28 @@ struct GroupLaunch {
                                cudaStream_t s) {
         k_marlin_scalars<FrP><<<(k + 1 + 31) / 32, 32, 0, s>>>(tab, powers_length, k, out_g2, out_alpha);
     }
+    // Groups with a lane-split twin (ec.cuh PairTwin): which kernels run it.  $SS_PAIR_KERNELS is a bit mask
+    // (1 = scalar multiplication, 2 = subgroup test, 4 = bucket accumulation), default 2: measured on B200 at 2^20
+    // (profiles/r02_ab_variants.md) the lane-split subgroup test is 4 % faster than the per-thread one (60.8 vs
+    // 63.3 ms: no table, 304-byte frame), the bucket accumulation equal (32.2 vs 32.3 ms) and the scalar multiplication
+    // SLOWER (185.6 ms at 255 registers, 207.6 at 168, vs 168.7) — its 8-entry table and the operand exchange keep the
+    // per-lane register pressure where the per-thread kernel already was.
+    static bool use_pair(int which) {
+        static const int mask = [] {
+            const char* e = getenv("SS_PAIR_KERNELS");
+            return e ? atoi(e) : 2;
+        }();
+        return (mask & which) != 0;
+    }
     static void scalar_mul(const ScalarMulArgs& a, cudaStream_t s) {
         if (!a.n) return;
+        using GL = typename PairTwin<G>::type;
+        if constexpr (!std::is_void<GL>::value) {
+            if (use_pair(1)) {
+                k_scalar_mul_pair<GL><<<(unsigned)((2 * a.n + SS_SMUL_TPB - 1) / SS_SMUL_TPB), SS_SMUL_TPB, 0, s>>>(a);
+                return;
+            }
+        }
         k_scalar_mul<G><<<(unsigned)((a.n + SS_SMUL_TPB - 1) / SS_SMUL_TPB), SS_SMUL_TPB, 0, s>>>(a);
     }
     static void normalize_encode(const NormalizeArgs& a, cudaStream_t s) {
@@ -521,6 +663,13 @@ struct GroupLaunch {
     }
     static void subgroup(const SubgroupArgs& a, cudaStream_t s) {
         if (!a.count) return;
+        using GL = typename PairTwin<G>::type;
+        if constexpr (!std::is_void<GL>::value) {
+            if (use_pair(2)) {
+                k_subgroup_pair<GL><<<(unsigned)((2 * a.count + 127) / 128), 128, 0, s>>>(a);
+                return;
+            }
+        }
         k_subgroup<G><<<(unsigned)((a.count + 127) / 128), 128, 0, s>>>(a);
     }
     static void sum_points(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status, cudaStream_t s) {

@@ -233,6 +233,74 @@ __global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_MSM_MINB_N
     store_jac<G>(a.buckets, NB, WB + t, jac_add(load_jac<G>(a.buckets, NB, WB + t), s2));
 }
 
+// lane-split twin: one bucket per lane pair (fp2l.cuh); bucket entries are read / written as their 48-byte halves
+template <class GL>
+SS_D Jac<typename GL::F> load_jac_half(const uint32_t* base, uint64_t i) {
+    using F = typename GL::F;
+    constexpr int HW = F::Base::N;
+    const int odd = lane_odd();
+    Jac<F> j;
+    const uint4* s = reinterpret_cast<const uint4*>(base + i * (6 * HW) + odd * HW);
+#pragma unroll
+    for (int k = 0; k < HW / 4; k++) {
+        const uint4 a = s[k], b = s[k + 2 * HW / 4], c = s[k + 4 * HW / 4];
+        j.X.h.l[4 * k] = a.x; j.X.h.l[4 * k + 1] = a.y; j.X.h.l[4 * k + 2] = a.z; j.X.h.l[4 * k + 3] = a.w;
+        j.Y.h.l[4 * k] = b.x; j.Y.h.l[4 * k + 1] = b.y; j.Y.h.l[4 * k + 2] = b.z; j.Y.h.l[4 * k + 3] = b.w;
+        j.Z.h.l[4 * k] = c.x; j.Z.h.l[4 * k + 1] = c.y; j.Z.h.l[4 * k + 2] = c.z; j.Z.h.l[4 * k + 3] = c.w;
+    }
+    return j;
+}
+template <class GL>
+SS_D void store_jac_half(uint32_t* base, uint64_t i, const Jac<typename GL::F>& j) {
+    using F = typename GL::F;
+    constexpr int HW = F::Base::N;
+    const int odd = lane_odd();
+    uint4* d = reinterpret_cast<uint4*>(base + i * (6 * HW) + odd * HW);
+#pragma unroll
+    for (int k = 0; k < HW / 4; k++) {
+        d[k] = make_uint4(j.X.h.l[4 * k], j.X.h.l[4 * k + 1], j.X.h.l[4 * k + 2], j.X.h.l[4 * k + 3]);
+        d[k + 2 * HW / 4] = make_uint4(j.Y.h.l[4 * k], j.Y.h.l[4 * k + 1], j.Y.h.l[4 * k + 2], j.Y.h.l[4 * k + 3]);
+        d[k + 4 * HW / 4] = make_uint4(j.Z.h.l[4 * k], j.Z.h.l[4 * k + 1], j.Z.h.l[4 * k + 2], j.Z.h.l[4 * k + 3]);
+    }
+}
+
+template <class GL>
+__global__ void __launch_bounds__(128, GL::SMUL_MINB) k_msm_accumulate_pair(MsmAccArgs a) {
+    using F = typename GL::F;
+    const uint32_t B = 1u << a.c;
+    const uint64_t WB = (uint64_t)a.W * B;
+    const uint64_t tid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    // converged-warp discipline (fp2l.cuh): no lane leaves early; a warp walks max(run length) steps — buckets are
+    // visited in order of decreasing run length, so the runs of one warp are (nearly) equal — and lanes whose run is
+    // over add the point at infinity
+    const bool valid = tid < WB;
+    const uint64_t t = valid ? a.order[tid] : 0;
+    const uint32_t d = (uint32_t)(t & (B - 1));
+    const bool active = valid && d != 0 && a.counts[t] != 0;
+    const uint32_t cnt = active ? a.counts[t] : 0u;
+    const int w = (int)(t >> a.c);
+    const uint32_t* list = a.idx + (size_t)w * a.n + (active ? a.offsets[t] : 0u);
+    const uint32_t steps = __reduce_max_sync(kFullMask, cnt);
+    Jac<F> s1 = Jac<F>::identity(), s2 = Jac<F>::identity();
+#pragma unroll 1
+    for (uint32_t k = 0; k < steps; k++) {
+        const bool on = k < cnt;
+        const uint32_t i = on ? list[k] : 0u;
+        Affine<F> q1 = load_affine_half<GL>(a.aff1, a.inf1, i);
+        Affine<F> q2 = load_affine_half<GL>(a.aff2, a.inf2, i);
+        q1.inf = q1.inf || !on;
+        q2.inf = q2.inf || !on;
+        s1 = jac_madd_inl(s1, q1);
+        s2 = jac_madd_inl(s2, q2);
+    }
+    const Jac<F> b1 = jac_add_inl(load_jac_half<GL>(a.buckets, t), s1);
+    const Jac<F> b2 = jac_add_inl(load_jac_half<GL>(a.buckets, WB + t), s2);
+    if (active) {
+        store_jac_half<GL>(a.buckets, t, b1);
+        store_jac_half<GL>(a.buckets, WB + t, b2);
+    }
+}
+
 // k * P for a small k (Jacobian base)
 template <class F>
 SS_D Jac<F> jac_mul_small(const Jac<F>& p, uint32_t k) {
@@ -339,6 +407,13 @@ struct MsmLaunch {
     }
     static void accumulate(const MsmAccArgs& a, cudaStream_t s) {
         const uint64_t wb = (uint64_t)a.W << a.c;
+        using GL = typename PairTwin<G>::type;
+        if constexpr (!std::is_void<GL>::value) {
+            if (GroupLaunch<G>::use_pair(4)) {
+                k_msm_accumulate_pair<GL><<<(unsigned)((2 * wb + 127) / 128), 128, 0, s>>>(a);
+                return;
+            }
+        }
         k_msm_accumulate<G><<<(unsigned)((wb + 127) / 128), 128, 0, s>>>(a);
     }
     static void reduce(const MsmReduceArgs& a, cudaStream_t s) {

@@ -5,6 +5,7 @@
 #include <cstring>
 #include "../../snark-setup_b200/csrc/codec.cuh"
 #include "../../snark-setup_b200/csrc/glv.cuh"
+#include "../../snark-setup_b200/csrc/fp2l.cuh"
 
 using namespace ss;
 
@@ -242,5 +243,45 @@ int emul_point_add(int group, const uint8_t* a, const uint8_t* b, int which, uin
         case 3: return point_add<Bw6G2>(a, b, which, out);
     }
     return -1;
+}
+
+// fp_mul2: (a*b + c*d) / R mod p on canonical inputs scaled as (a, c) < scale_ac * p and (b, d) < scale_bd * p is NOT
+// needed here: the inputs are plain residues; `a2`/`c2` flags add p to a / c first (operands below 2p are allowed)
+int emul_fp_mul2(const uint8_t* a, const uint8_t* b, const uint8_t* c, const uint8_t* d, int a_plus_p, int d_times5, uint8_t* out) {
+    typedef Bls377Fq P;
+    Fp<P> x = fp_to_mont(load_raw<P>(a)), y = fp_to_mont(load_raw<P>(b)), z = fp_to_mont(load_raw<P>(c)), w = fp_to_mont(load_raw<P>(d));
+    if (a_plus_p) {  // unreduced representative x + p (< 2p): same residue, exercises the operand bound
+        Fp<P> m;
+        for (int i = 0; i < P::N; i++) m.l[i] = P::mod(i);
+        x = fp_add_nr(x, m);
+        z = fp_add_nr(z, m);
+    }
+    if (d_times5) {  // unreduced 5*w (< 5p) as the scanned operand
+        Fp<P> t = fp_add_nr(w, w);
+        t = fp_add_nr(t, t);
+        w = fp_add_nr(t, w);
+    }
+    Fp<P> r = fp_mul2(x, y, z, w);
+    store_raw<P>(out, fp_from_mont(r));
+    return 0;
+}
+
+// lane-split Fq2 product / square through the pure per-lane functions of fp2l.cuh: both lanes evaluated in turn
+int emul_fp2l_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    typedef Bls377Fq P;
+    Fp<P> a0 = fp_to_mont(load_raw<P>(a)), a1 = fp_to_mont(load_raw<P>(a + 48));
+    Fp<P> b0 = fp_to_mont(load_raw<P>(b)), b1 = fp_to_mont(load_raw<P>(b + 48));
+    Fp<P> r0, r1;
+    if (op == 0) {
+        r0 = fp2l_mul_lane<P>(0, a0, a1, b0, b1);
+        r1 = fp2l_mul_lane<P>(1, a1, a0, b1, b0);
+    } else {
+        Fp<P> p0 = fp2l_sqr_lane1<P>(0, a0, a1), p1 = fp2l_sqr_lane1<P>(1, a1, a0);
+        r0 = fp2l_sqr_lane2<P>(0, p0, p1);
+        r1 = fp2l_sqr_lane2<P>(1, p1, p0);
+    }
+    store_raw<P>(out, fp_from_mont(r0));
+    store_raw<P>(out + 48, fp_from_mont(r1));
+    return 0;
 }
 }

@@ -122,3 +122,50 @@ def test_points(L, gid):
     bad = bytearray(b"\xff" * g.csize)
     bad[-1] = 0x3F
     assert L.emul_point_mul(gid, bytes(bad), 1, R.NO, tb(5, nb), 8, out, 0) == 1
+
+
+def test_fp_mul2_sum_of_two_products(L):
+    """fp_mul2 = (a b + c d) / R with one interleaved reduction (fp.cuh), incl. operands at their documented bounds:
+    a, c up to 2p and the scanned operand d up to 5p."""
+    p, nb = FIELDS[0]
+    rng = random.Random(77)
+    for it in range(60):
+        a, b, c, d = (rng.randrange(p) for _ in range(4))
+        if it == 0:
+            a = b = c = d = p - 1
+        if it == 1:
+            a, b, c, d = 0, 0, p - 1, p - 1
+        if it == 2:
+            a, b, c, d = p - 1, 1, 1, p - 1
+        for a_plus_p in (0, 1):
+            for d5 in (0, 1):
+                out = ctypes.create_string_buffer(nb)
+                assert L.emul_fp_mul2(tb(a, nb), tb(b, nb), tb(c, nb), tb(d, nb), a_plus_p, d5, out) == 0
+                want = (a * b + c * (5 * d if d5 else d)) % p
+                assert out.raw == tb(want, nb), (it, a_plus_p, d5)
+
+
+def test_lane_split_fq2_product_and_square(L):
+    """fp2l.cuh: the per-lane halves of the Fq2 product / square (even lane a0 b0 - 5 a1 b1, odd lane a0 b1 + a1 b0;
+    complex squaring split as (a0 + a1)(a0 - 5 a1) | a0 a1) against the big-integer Fq2."""
+    p, nb = FIELDS[0]
+    F2 = R.BLS12_377.g2.F
+    rng = random.Random(78)
+    for it in range(60):
+        a = (rng.randrange(p), rng.randrange(p))
+        b = (rng.randrange(p), rng.randrange(p))
+        if it == 0:
+            a = b = (p - 1, p - 1)
+        if it == 1:
+            a, b = (0, p - 1), (p - 1, 0)
+        if it == 2:
+            a, b = (0, 0), (5, 7)
+        ab = tb(a[0], nb) + tb(a[1], nb)
+        bb = tb(b[0], nb) + tb(b[1], nb)
+        out = ctypes.create_string_buffer(2 * nb)
+        assert L.emul_fp2l_op(0, ab, bb, out) == 0
+        m = F2.mul(a, b)
+        assert out.raw == tb(m[0], nb) + tb(m[1], nb), it
+        assert L.emul_fp2l_op(1, ab, bb, out) == 0
+        q = F2.sqr(a)
+        assert out.raw == tb(q[0], nb) + tb(q[1], nb), it
