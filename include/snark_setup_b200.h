@@ -13,9 +13,9 @@
  *   - Points cross the boundary in the reference's canonical serialisation (ark-serialize 0.4):
  *     packed elements, no header; `compressed` selects x+flags vs x||y+flags
  *     (sizes: BLS12-377 G1 48/96, G2 96/192; BW6-761 G1 = G2 = 96/192,
- *     phase1/src/objects/parameters.rs:312-317).
+ *     phase1/src/objects/parameters.rs:312-317; MNT4-753 G1 95/190, G2 190/380; MNT6-753 G1 95/190, G2 285/570).
  *   - Scalars cross as canonical little-endian integers < r of ss_scalar_size() bytes
- *     (32 for BLS12-377, 48 for BW6-761) = `Fr::serialize_uncompressed`.
+ *     (32 for BLS12-377, 48 for BW6-761, 95 for MNT4/6-753) = `Fr::serialize_uncompressed`.
  *   - `check` is setup_utils::CheckForCorrectness (setup-utils/src/elements.rs:18-23).
  *   - Return value: SS_OK or an ss_status error; details of the last error of the calling thread
  *     via ss_last_error().  Errors map 1:1 onto setup_utils::Error (setup-utils/src/errors.rs:11-38).
@@ -35,7 +35,13 @@
 extern "C" {
 #endif
 
-typedef enum { SS_CURVE_BLS12_377 = 0, SS_CURVE_BW6_761 = 1 } ss_curve;
+/* The curves the reference exposes (setup-utils/src/converters.rs:18-45).  BLS12-377 and BW6-761 are the tuned ceremony
+ * curves.  MNT4-753 / MNT6-753 (a != 0, G2 over Fq2 / Fq3, 95-byte field elements) run the same entry points
+ * functionally — batch_exp / apply_powers / Phase1::computation, transcode, subgroup checks, merge_pairs / power_pairs
+ * and the verification vectors — without endomorphism speed-ups; not available for them: ss_phase1_initialization (the
+ * arkworks G2 generator constants are not known to this build), the device pairing checks (ss_*same_ratio*; the (s, sx)
+ * pairs are returned for the host's check_same_ratio as SURVEY.md §8 A12 places it), group FFT and QAP. */
+typedef enum { SS_CURVE_BLS12_377 = 0, SS_CURVE_BW6_761 = 1, SS_CURVE_MNT4_753 = 2, SS_CURVE_MNT6_753 = 3 } ss_curve;
 typedef enum { SS_G1 = 0, SS_G2 = 1 } ss_group;
 
 /* setup_utils::CheckForCorrectness (setup-utils/src/elements.rs:18-23) */

@@ -229,18 +229,126 @@ class Fp2:
         return (c0, c1), flags
 
 
+class Fp3:
+    """Fp[u]/(u^3 - nr); elements are (c0, c1, c2)  (ark-ff CubicExtField, used by MNT6-753 G2)."""
+
+    degree = 3
+
+    def __init__(self, base: Fp, nr: int):
+        self.b = base
+        self.p = base.p
+        self.nr = nr % base.p
+        self.zero = (0, 0, 0)
+        self.one = (1, 0, 0)
+        self.bits = base.bits
+        # Tonelli-Shanks data for the multiplicative group of order p^3 - 1 = 2^s * t
+        n = self.p ** 3 - 1
+        self.s = 0
+        while n % 2 == 0:
+            n //= 2
+            self.s += 1
+        self.t = n
+        self._z = None
+
+    def add(self, a, b): return tuple((x + y) % self.p for x, y in zip(a, b))
+    def sub(self, a, b): return tuple((x - y) % self.p for x, y in zip(a, b))
+    def neg(self, a): return tuple((-x) % self.p for x in a)
+
+    def mul(self, a, b):
+        p, nr = self.p, self.nr
+        a0, a1, a2 = a
+        b0, b1, b2 = b
+        return ((a0 * b0 + nr * (a1 * b2 + a2 * b1)) % p,
+                (a0 * b1 + a1 * b0 + nr * a2 * b2) % p,
+                (a0 * b2 + a1 * b1 + a2 * b0) % p)
+
+    def sqr(self, a): return self.mul(a, a)
+
+    def pow(self, a, e):
+        r = self.one
+        for bit in bin(e)[2:]:
+            r = self.mul(r, r)
+            if bit == "1":
+                r = self.mul(r, a)
+        return r
+
+    def inv(self, a):
+        # a^-1 = a^(p^3 - 2); slow but this is the oracle
+        return self.pow(a, self.p ** 3 - 2)
+
+    def is_zero(self, a): return a == (0, 0, 0)
+    def from_int(self, v): return (v % self.p, 0, 0)
+
+    def sqrt(self, a):
+        """Any square root or None (Tonelli-Shanks in Fp3*)."""
+        if a == self.zero:
+            return a
+        if self.pow(a, (self.p ** 3 - 1) // 2) != self.one:
+            return None
+        if self._z is None:
+            c = 1
+            while True:  # a quadratic non-residue of the form (c, 1, 0)
+                cand = (c, 1, 0)
+                if self.pow(cand, (self.p ** 3 - 1) // 2) != self.one:
+                    break
+                c += 1
+            self._z = self.pow(cand, self.t)
+        z, v = self._z, self.s
+        w = self.pow(a, (self.t - 1) // 2)
+        x = self.mul(a, w)
+        b = self.mul(x, w)
+        while b != self.one:
+            k, b2k = 0, b
+            while b2k != self.one:
+                b2k = self.sqr(b2k)
+                k += 1
+            wj = z
+            for _ in range(v - k - 1):
+                wj = self.sqr(wj)
+            z = self.sqr(wj)
+            b = self.mul(b, z)
+            x = self.mul(x, wj)
+            v = k
+        assert self.sqr(x) == a
+        return x
+
+    def gt(self, a, b):
+        """Lexicographic, c2 first, then c1, then c0 (ark-ff CubicExtField Ord)."""
+        for i in (2, 1, 0):
+            if a[i] != b[i]:
+                return a[i] > b[i]
+        return False
+
+    def size(self, flag_bits=0):
+        return 2 * self.b.size(0) + self.b.size(flag_bits)
+
+    def to_bytes(self, a, flags=0, flag_bits=0):
+        return self.b.to_bytes(a[0]) + self.b.to_bytes(a[1]) + self.b.to_bytes(a[2], flags, flag_bits)
+
+    def from_bytes(self, b, flag_bits=0):
+        n0 = self.b.size(0)
+        c0, _ = self.b.from_bytes(b[:n0], 0)
+        c1, _ = self.b.from_bytes(b[n0:2 * n0], 0)
+        c2, flags = self.b.from_bytes(b[2 * n0:], flag_bits)
+        return (c0, c1, c2), flags
+
+
 # ----------------------------------------------------------------------------------------------
-# short-Weierstrass groups, a = 0
+# short-Weierstrass groups (a = 0 for BLS12-377 / BW6-761, a != 0 for the MNT curves)
 # ----------------------------------------------------------------------------------------------
 FLAG_NEG = 0x80   # SWFlags::YIsNegative
 FLAG_INF = 0x40   # SWFlags::PointAtInfinity
 
 
 class Group:
-    """y^2 = x^3 + b over field F (a = 0). Points: None (identity) or (x, y)."""
+    """y^2 = x^3 + a x + b over field F (a = 0 unless given). Points: None (identity) or (x, y)."""
 
-    def __init__(self, name, F, b, gen, r):
+    def __init__(self, name, F, b, gen, r, a=None, gen_is_reference=True):
         self.name, self.F, self.b, self.gen, self.r = name, F, b, gen, r
+        self.a = F.zero if a is None else a
+        self.a_is_zero = F.is_zero(self.a)
+        # False when `gen` is only SOME generator of the order-r group (the reference's constant is unknown here)
+        self.gen_is_reference = gen_is_reference
         self.usize = 2 * F.size(0) if F.degree == 1 else F.size(0) + F.size(2)
         self.usize = F.size(0) + F.size(2)
         self.csize = F.size(2)
@@ -251,7 +359,12 @@ class Group:
             return True
         F = self.F
         x, y = P
-        return F.sqr(y) == F.add(F.mul(F.sqr(x), x), self.b)
+        return F.sqr(y) == self.rhs(x)
+
+    def rhs(self, x):
+        """x^3 + a x + b"""
+        F = self.F
+        return F.add(F.mul(F.add(F.sqr(x), self.a), x), self.b)
 
     def neg(self, P):
         return None if P is None else (P[0], self.F.neg(P[1]))
@@ -267,7 +380,7 @@ class Group:
                 if F.is_zero(P[1]):
                     return None
                 x2 = F.sqr(P[0])
-                lam = F.mul(F.add(F.add(x2, x2), x2), F.inv(F.add(P[1], P[1])))
+                lam = F.mul(F.add(F.add(F.add(x2, x2), x2), self.a), F.inv(F.add(P[1], P[1])))
             else:
                 return None
         else:
@@ -311,6 +424,17 @@ class Group:
         F = self.F
         if F.is_zero(Z) or F.is_zero(Y):
             return (F.one, F.one, F.zero)
+        if not self.a_is_zero:  # dbl-2007-bl
+            XX, YY, ZZ = F.sqr(X), F.sqr(Y), F.sqr(Z)
+            YYYY = F.sqr(YY)
+            t = F.sub(F.sub(F.sqr(F.add(X, YY)), XX), YYYY)
+            S = F.add(t, t)
+            M = F.add(F.add(F.add(XX, XX), XX), F.mul(self.a, F.sqr(ZZ)))
+            X3 = F.sub(F.sqr(M), F.add(S, S))
+            Y8 = F.add(YYYY, YYYY); Y8 = F.add(Y8, Y8); Y8 = F.add(Y8, Y8)
+            Y3 = F.sub(F.mul(M, F.sub(S, X3)), Y8)
+            Z3 = F.sub(F.sub(F.sqr(F.add(Y, Z)), YY), ZZ)
+            return (X3, Y3, Z3)
         A = F.sqr(X)
         B = F.sqr(Y)
         C = F.sqr(B)
@@ -380,9 +504,9 @@ class Group:
             if fl & FLAG_INF:
                 P = None
             else:
-                y = F.sqrt(F.add(F.mul(F.sqr(x), x), self.b))
+                y = F.sqrt(self.rhs(x))
                 if y is None:
-                    raise InvalidData("x^3+b is not a square")
+                    raise InvalidData("x^3+ax+b is not a square")
                 ny = F.neg(y)
                 lo, hi = (y, ny) if F.gt(ny, y) else (ny, y)
                 P = (x, hi if fl & FLAG_NEG else lo)
@@ -455,9 +579,80 @@ def _mk_bw6_761():
     return Curve("bw6_761", g1, g2, BLS12_377_Q)
 
 
+# MNT4-753 / MNT6-753 (setup-utils/src/converters.rs:18-45 exposes both).  The two 753-bit primes form a cycle:
+# MNT4: Fq = MNT753_Q, Fr = MNT753_R;  MNT6: Fq = MNT753_R, Fr = MNT753_Q.  Curve coefficients and the G1 generators are
+# the ark-mnt4-753 / ark-mnt6-753 0.4.0 constants as recalled; they are VERIFIED here, not trusted
+# (tests/test_oracle_mnt_cpu.py): both curves have prime order = the other prime (r * P = O for random points, so the
+# G1 cofactor is 1), the generators lie on their curves, 13 is a quadratic non-residue mod MNT753_Q and 11 a cubic
+# non-residue mod MNT753_R, and the twists E'(Fq2) / E'(Fq3) have order divisible by r.  The G2 GENERATOR constants of
+# arkworks could not be recalled: `gen` of the two G2 groups is a deterministically derived point of order r
+# (gen_is_reference = False) — good for tests, not for Phase1::initialization, whose output must be arkworks' constant.
+MNT753_Q = 41898490967918953402344214791240637128170709919953949071783502921025352812571106773058893763790338921418070971888253786114353726529584385201591605722013126468931404347949840543007986327743462853720628051692141265303114721689601
+MNT753_R = 41898490967918953402344214791240637128170709919953949071783502921025352812571106773058893763790338921418070971888458477323173057491593855069696241854796396165721416325350064441470418137846398469611935719059908164220784476160001
+MNT4_B = 28798803903456388891410036793299405764940372360099938340752576406393880372126970068421383312482853541572780087363938442377933706865252053507077543420534380486492786626556269083255657125025963825610840222568694137138741554679540
+MNT6_B = 11625908999541321152027340224010374716841167701783584648338908235410859267060079819722747939267925389062611062156601938166010098747920378738927832658133625454260115409075816187555055859490253375704728027944315501122723426879114
+
+
+def _derive_generator(group, cofactor):
+    """first x = (counter, 1, ..) with a point on the curve, cofactor-cleared: SOME generator of the order-r group"""
+    F = group.F
+    c = 1
+    while True:
+        x = c if F.degree == 1 else ((c, 1) if F.degree == 2 else (c, 1, 0))
+        y = F.sqrt(group.rhs(x))
+        if y is not None:
+            P = group.mul((x, y), cofactor)
+            if P is not None:
+                return P
+        c += 1
+
+
+def _mk_mnt4_753():
+    fq = Fp(MNT753_Q)
+    fq2 = Fp2(fq, 13)
+    g1 = Group("mnt4_753.g1", fq, MNT4_B,
+               (7790163481385331313124631546957228376128961350185262705123068027727518350362064426002432450801002268747950550964579198552865939244360469674540925037890082678099826733417900510086646711680891516503232107232083181010099241949569,
+                6913648190367314284606685101150155872986263667483624713540251048208073654617802840433842931301128643140890502238233930290161632176167186761333725658542781350626799660920481723757654531036893265359076440986158843531053720994648),
+               MNT753_R, a=2)
+    # twist by u (u^2 = 13): a' = a u^2 = 26, b' = b u^3 = 13 b u
+    g2 = Group("mnt4_753.g2", fq2, (0, 13 * MNT4_B % MNT753_Q), None, MNT753_R, a=(26, 0), gen_is_reference=False)
+    t = MNT753_Q + 1 - MNT753_R
+    g2.order_full = MNT753_Q ** 2 + 1 + (t * t - 2 * MNT753_Q)  # quadratic twist of E(Fq2)
+    g2.cofactor = g2.order_full // MNT753_R
+    g2.gen = _derive_generator(g2, g2.cofactor)
+    return Curve("mnt4_753", g1, g2, MNT753_R)
+
+
+def _mk_mnt6_753():
+    fq = Fp(MNT753_R)
+    fq3 = Fp3(fq, 11)
+    g1 = Group("mnt6_753.g1", fq, MNT6_B,
+               (3458420969484235708806261200128850544017070333833944116801482064540723268149235477762870414664917360605949659630933184751526227993647030875167687492714052872195770088225183259051403087906158701786758441889742618916006546636728,
+                27460508402331965149626600224382137254502975979168371111640924721589127725376473514838234361114855175488242007431439074223827742813911899817930728112297763448010814764117701403540298764970469500339646563344680868495474127850569),
+               MNT753_Q, a=11)
+    # twist by u (u^3 = 11): a' = a u^2 = (0, 0, 11), b' = b u^3 = 11 b
+    g2 = Group("mnt6_753.g2", fq3, (11 * MNT6_B % MNT753_R, 0, 0), None, MNT753_Q, a=(0, 0, 11), gen_is_reference=False)
+    q = MNT753_R
+    t = q + 1 - MNT753_Q
+    t3 = t ** 3 - 3 * q * t
+    g2.order_full = q ** 3 + 1 + t3  # quadratic twist of E(Fq3)
+    g2.cofactor = g2.order_full // MNT753_Q
+    g2.gen = _derive_generator(g2, g2.cofactor)
+    return Curve("mnt6_753", g1, g2, MNT753_Q)
+
+
 BLS12_377 = _mk_bls12_377()
 BW6_761 = _mk_bw6_761()
 CURVES = {"bls12_377": BLS12_377, "bw6_761": BW6_761}
+_LAZY = {"mnt4_753": _mk_mnt4_753, "mnt6_753": _mk_mnt6_753}
+
+
+def curve_by_name(name):
+    """BLS12-377 / BW6-761 are built at import; the MNT curves on first use (their G2 generators take a cofactor
+    multiplication to derive)."""
+    if name not in CURVES:
+        CURVES[name] = _LAZY[name]()
+    return CURVES[name]
 
 
 # ----------------------------------------------------------------------------------------------

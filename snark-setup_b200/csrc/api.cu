@@ -60,7 +60,22 @@ int fail(int code, uint64_t index, uint64_t expected, uint64_t got, const char* 
 const GroupOps* group_ops(int curve, int group) {
     if (curve == SS_CURVE_BLS12_377) return group == SS_G1 ? &ops_bls377_g1() : group == SS_G2 ? &ops_bls377_g2() : nullptr;
     if (curve == SS_CURVE_BW6_761) return group == SS_G1 ? &ops_bw6_g1() : group == SS_G2 ? &ops_bw6_g2() : nullptr;
+    if (curve == SS_CURVE_MNT4_753) return group == SS_G1 ? &ops_mnt4_g1() : group == SS_G2 ? &ops_mnt4_g2() : nullptr;
+    if (curve == SS_CURVE_MNT6_753) return group == SS_G1 ? &ops_mnt6_g1() : group == SS_G2 ? &ops_mnt6_g2() : nullptr;
     return nullptr;
+}
+
+// Scalars cross the ABI as ceil(bits / 8) canonical bytes (95 for the MNT curves); on the device every scalar occupies
+// fr_words whole words.  Arrays of host scalars whose size is not a multiple of 4 are re-packed to that stride before
+// the upload (`keep` owns the staging copy until the stream has been synchronised).
+size_t scalar_stride(const GroupOps& o) { return (size_t)o.fr_words * 4; }
+const uint8_t* repack_scalars(const GroupOps& o, const uint8_t* src, size_t n, std::vector<std::vector<uint8_t>>& keep) {
+    const size_t fb = o.fr_bytes, fs = scalar_stride(o);
+    if (fb == fs) return src;
+    keep.emplace_back(n * fs, 0);
+    uint8_t* dst = keep.back().data();
+    for (size_t i = 0; i < n; i++) memcpy(dst + i * fs, src + i * fb, fb);
+    return dst;
 }
 
 // ---- per-kernel timing (ss_profile_*) -----------------------------------------------------------
@@ -320,7 +335,9 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
     const int nl = (host && ntiles > 1) ? 2 : 1;
     size_t per_lane = scratch_bytes(o, T) + 256;
     const bool stage_exps = host && j.exps && !j.exps_on_device;
-    if (host) per_lane += align_up(isz * T, 256) + align_up(osz * T, 256) + (stage_exps ? align_up((size_t)o.fr_bytes * T, 256) : 0);
+    const size_t fs = scalar_stride(o);
+    std::vector<std::vector<uint8_t>> keep;
+    if (host) per_lane += align_up(isz * T, 256) + align_up(osz * T, 256) + (stage_exps ? align_up(fs * T, 256) : 0);
     LaneGuard lg[2];
     for (int k = 0; k < nl; k++) {
         int rc = lane_acquire(device, per_lane + ntiles * 8 + 256, &lg[k].l);
@@ -356,18 +373,19 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
             uint8_t* bo = cv.take<uint8_t>(osz * T);
             CU(cudaMemcpyAsync(bi, j.in + e0 * isz, cnt * isz, cudaMemcpyHostToDevice, s));
             if (stage_exps) {
-                uint8_t* be = cv.take<uint8_t>((size_t)o.fr_bytes * T);
-                CU(cudaMemcpyAsync(be, j.exps + e0 * o.fr_bytes, cnt * o.fr_bytes, cudaMemcpyHostToDevice, s));
+                uint8_t* be = cv.take<uint8_t>(fs * T);
+                const uint8_t* src = repack_scalars(o, j.exps + e0 * o.fr_bytes, cnt, keep);
+                CU(cudaMemcpyAsync(be, src, cnt * fs, cudaMemcpyHostToDevice, s));
                 d_exps = be;
             } else if (j.exps) {
-                d_exps = j.exps + e0 * o.fr_bytes;
+                d_exps = j.exps + e0 * fs;  // already on the device, word stride
             }
             d_in = bi;
             d_out = bo;
         } else {
             d_in = j.in + e0 * isz;
             d_out = j.out + e0 * osz;
-            if (j.exps) d_exps = j.exps + e0 * o.fr_bytes;
+            if (j.exps) d_exps = j.exps + e0 * fs;
         }
         DecodeArgs da;
         da.in = reinterpret_cast<const uint32_t*>(d_in);
@@ -422,6 +440,7 @@ struct ScalarSetup {
         const size_t fb = o.fr_bytes, fw = o.fr_words;
         const size_t tab_b = align_up(64 * fw * 4, 256), el_b = align_up(fw * 4, 256);
         CU(cudaMalloc(&slab, tab_b + 3 * el_b + 4 * el_b));
+        CU(cudaMemsetAsync(slab, 0, tab_b + 3 * el_b + 4 * el_b, s));  // scalars of 95 bytes leave a partial top word
         d_tab = reinterpret_cast<uint32_t*>(slab);
         uint8_t* p = slab + tab_b;
         for (int k = 0; k < 3; k++) d_coeff_m[k] = reinterpret_cast<uint32_t*>(p + k * el_b);
@@ -441,22 +460,39 @@ struct ScalarSetup {
     }
 };
 
-// r for BLS12-377 (8 words) / BW6-761 (12 words), little-endian u32 limbs
+// the scalar-field modulus r of a curve, little-endian u32 limbs
 const uint32_t* scalar_modulus(int curve, int* n) {
     static const uint32_t r_bls[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
     static const uint32_t r_bw6[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
-    *n = curve == SS_CURVE_BLS12_377 ? 8 : 12;
-    return curve == SS_CURVE_BLS12_377 ? r_bls : r_bw6;
+    static uint32_t r_mnt[2][24];
+    static const bool init = [] {  // MNT4 Fr = Mnt753R, MNT6 Fr = Mnt753Q (constants_gen.cuh)
+        for (int i = 0; i < 24; i++) {
+            r_mnt[0][i] = Mnt753R::mod(i);
+            r_mnt[1][i] = Mnt753Q::mod(i);
+        }
+        return true;
+    }();
+    (void)init;
+    switch (curve) {
+        case SS_CURVE_BLS12_377: *n = 8; return r_bls;
+        case SS_CURVE_BW6_761: *n = 12; return r_bw6;
+        case SS_CURVE_MNT4_753: *n = 24; return r_mnt[0];
+        case SS_CURVE_MNT6_753: *n = 24; return r_mnt[1];
+    }
+    *n = 0;
+    return nullptr;
 }
 
 bool scalar_is_canonical(int curve, const uint8_t* s) {
     int n;
     const uint32_t* r = scalar_modulus(curve, &n);
+    if (!r) return false;
+    const GroupOps* o = group_ops(curve, SS_G1);
+    uint32_t w[24] = {0};
+    memcpy(w, s, o->fr_bytes);  // 95-byte scalars: the top word is zero-extended
     for (int i = n - 1; i >= 0; i--) {
-        uint32_t w;
-        memcpy(&w, s + 4 * i, 4);
-        if (w < r[i]) return true;
-        if (w > r[i]) return false;
+        if (w[i] < r[i]) return true;
+        if (w[i] > r[i]) return false;
     }
     return false;
 }
@@ -539,7 +575,7 @@ int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& 
     const uint64_t n_g2 = chunk0 ? k + 2 : 0, n_al = chunk0 ? 3 + 3 * k : 0;
     auto sz = [&](const GroupOps& g, int c) { return (uint64_t)(c ? g.csize : g.usize); };
     LaneGuard lane;
-    if ((rc = lane_acquire(device, 4096 + (n_g2 + n_al) * g1.fr_bytes, &lane.l))) return rc;
+    if ((rc = lane_acquire(device, 4096 + (n_g2 + n_al) * scalar_stride(g1), &lane.l))) return rc;
     ScalarSetup sc;
     const uint8_t* coeffs[3] = {nullptr, alpha, nullptr};
     if ((rc = sc.init(g1, tau, coeffs, lane.l->stream))) return rc;
@@ -556,7 +592,7 @@ int phase1_computation_marlin(const ss_phase1_params* p, const ss_phase1_sizes& 
     }
     if (!chunk0 || shard_index != 0) return SS_OK;
     uint8_t* d_g2s = lane.l->buf;
-    uint8_t* d_als = d_g2s + align_up(n_g2 * g1.fr_bytes, 256);
+    uint8_t* d_als = d_g2s + align_up(n_g2 * scalar_stride(g1), 256);
     g1.marlin_scalars(sc.d_tab, z.powers_length, (int)k, reinterpret_cast<uint32_t*>(d_g2s), reinterpret_cast<uint32_t*>(d_als),
                       lane.l->stream);
     CU(cudaGetLastError());
@@ -783,14 +819,22 @@ int ss_generate_powers_of_tau(int curve, const uint8_t* tau, uint64_t start, uin
     const int device = g_devices[0];
     const uint64_t n = end - start;
     LaneGuard lg;
-    if ((rc = lane_acquire(device, n * o->fr_bytes + 256, &lg.l))) return rc;
+    const size_t fs = scalar_stride(*o), fb = o->fr_bytes;
+    if ((rc = lane_acquire(device, n * fs + 256, &lg.l))) return rc;
     ScalarSetup sc;
     const uint8_t* coeffs[3] = {nullptr, nullptr, nullptr};
     if ((rc = sc.init(*o, tau, coeffs, lg.l->stream))) return rc;
     o->powers(sc.d_tab, start, n, reinterpret_cast<uint32_t*>(lg.l->buf), lg.l->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, lg.l->buf, n * o->fr_bytes, cudaMemcpyDeviceToHost, lg.l->stream));
-    CU(cudaStreamSynchronize(lg.l->stream));
+    if (fs == fb) {
+        CU(cudaMemcpyAsync(out, lg.l->buf, n * fb, cudaMemcpyDeviceToHost, lg.l->stream));
+        CU(cudaStreamSynchronize(lg.l->stream));
+    } else {  // device words -> packed ceil(bits / 8)-byte scalars
+        std::vector<uint8_t> tmp(n * fs);
+        CU(cudaMemcpyAsync(tmp.data(), lg.l->buf, n * fs, cudaMemcpyDeviceToHost, lg.l->stream));
+        CU(cudaStreamSynchronize(lg.l->stream));
+        for (uint64_t i = 0; i < n; i++) memcpy(out + i * fb, tmp.data() + i * fs, fb);
+    }
     return SS_OK;
 }
 
@@ -1042,14 +1086,17 @@ int ss_phase1_initialization(const ss_phase1_params* p, uint8_t* output, size_t 
     for (int v = 0; v < 5; v++) off[v + 1] = off[v] + cnt[v] * (grp[v] ? s2 : s1);
     const uint64_t need = off[5];
     if (output_len < need) return fail(SS_ERR_INVALID_LENGTH, 0, need, output_len, "output buffer too short");
+    if (!gs[0]->has_generator || !gs[1]->has_generator)
+        return fail(SS_ERR_INVALID_ARGUMENT, 0, 0, 0, "the reference's generator constant of %s is not known to this build",
+                    gs[0]->has_generator ? gs[1]->name : gs[0]->name);
     if ((rc = ensure_init())) return rc;
     LaneGuard lg;
-    if ((rc = lane_acquire(g_devices[0], 1024, &lg.l))) return rc;
-    uint8_t gen[2][192];
+    if ((rc = lane_acquire(g_devices[0], 4096, &lg.l))) return rc;
+    uint8_t gen[2][576];
     for (int g = 0; g < 2; g++) {
-        gs[g]->generator(reinterpret_cast<uint32_t*>(lg.l->buf) + g * 64, compressed_output, lg.l->stream);
+        gs[g]->generator(reinterpret_cast<uint32_t*>(lg.l->buf) + g * 256, compressed_output, lg.l->stream);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(gen[g], lg.l->buf + g * 256, g ? s2 : s1, cudaMemcpyDeviceToHost, lg.l->stream));
+        CU(cudaMemcpyAsync(gen[g], lg.l->buf + g * 1024, g ? s2 : s1, cudaMemcpyDeviceToHost, lg.l->stream));
     }
     CU(cudaStreamSynchronize(lg.l->stream));
     auto fill = [&](uint8_t* dst, const uint8_t* el, uint64_t sz, uint64_t count) {

@@ -31,7 +31,7 @@ int same_ratio_batch(int curve, const uint8_t* g1_pairs, const uint8_t* g2_pairs
     CU(cudaMemcpyAsync(d1, g1_pairs, b1, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d2, g2_pairs, b2, cudaMemcpyHostToDevice, s));
     {
-        ProfScope ps("k_same_ratio", curve == SS_CURVE_BLS12_377 ? "bls12_377" : "bw6_761", count, s);
+        ProfScope ps("k_same_ratio", curve == SS_CURVE_BLS12_377 ? "bls12_377" : "bw6_761", count, s);  // (no MNT pairing: pairing_ops() is null)
         po->same_ratio(reinterpret_cast<const uint32_t*>(d1), reinterpret_cast<const uint32_t*>(d2), count, dv, s);
     }
     CU(cudaGetLastError());

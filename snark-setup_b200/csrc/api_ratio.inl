@@ -18,6 +18,8 @@ namespace {
 const MsmOps* msm_ops(int curve, int group) {
     if (curve == SS_CURVE_BLS12_377) return group == SS_G1 ? &msm_ops_bls377_g1() : group == SS_G2 ? &msm_ops_bls377_g2() : nullptr;
     if (curve == SS_CURVE_BW6_761) return group == SS_G1 ? &msm_ops_bw6_g1() : group == SS_G2 ? &msm_ops_bw6_g2() : nullptr;
+    if (curve == SS_CURVE_MNT4_753) return group == SS_G1 ? &msm_ops_mnt4_g1() : group == SS_G2 ? &msm_ops_mnt4_g2() : nullptr;
+    if (curve == SS_CURVE_MNT6_753) return group == SS_G1 ? &msm_ops_mnt6_g1() : group == SS_G2 ? &msm_ops_mnt6_g2() : nullptr;
     return nullptr;
 }
 
@@ -86,7 +88,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     if (!j.rho) {
         nbits = ((128 + c - 1) / c) * c;
     } else {
-        nbits = j.curve == SS_CURVE_BLS12_377 ? 253 : 377;
+        nbits = o.fr_bits;
         while (c > 2 && !(nbits % c == 0 || nbits % c >= c - 1)) c--;
     }
     const int W = (nbits + c - 1) / c;
@@ -101,12 +103,13 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     if (host) need += (two ? 2 : 1) * align_up(isz * (T + 1), 256) + (j.out ? align_up(osz * T, 256) : 0);
     size_t sort_b = 0, bucket_b = 0;
     if (j.do_ratio) {
-        sort_b = 4 * align_up((size_t)W * B * 4, 256) + 1024 + align_up((size_t)W * T * 4, 256) + (j.rho ? align_up((size_t)o.fr_bytes * T, 256) : 0);
+        sort_b = 4 * align_up((size_t)W * B * 4, 256) + 1024 + align_up((size_t)W * T * 4, 256) + (j.rho ? align_up(scalar_stride(o) * T, 256) : 0);
         bucket_b = align_up((size_t)3 * fw * 4 * 2 * W * B, 256) + align_up((size_t)3 * fw * 4 * 2 * W * nseg, 256) +
                    align_up((size_t)3 * fw * 4 * 2 * W, 256) + 2 * align_up(o.usize, 256);
     }
     need += sort_b + bucket_b;
     LaneGuard lg;
+    std::vector<std::vector<uint8_t>> keep;  // re-packed scalar staging, alive until the stream is synchronised
     int rc = lane_acquire(device, need, &lg.l);
     if (rc) return rc;
     cudaStream_t s = (!host && user_stream) ? user_stream : lg.l->stream;
@@ -136,7 +139,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
         order = cv.take<uint32_t>((size_t)W * B * 4);
         bins = cv.take<uint32_t>(1024);
         idx = cv.take<uint32_t>((size_t)W * T * 4);
-        if (j.rho) d_rho = cv.take<uint8_t>((size_t)o.fr_bytes * T);
+        if (j.rho) d_rho = cv.take<uint8_t>(scalar_stride(o) * T);
         buckets = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W * B);
         segres = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W * nseg);
         winres = cv.take<uint32_t>((size_t)3 * fw * 4 * 2 * W);
@@ -185,7 +188,8 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
             MsmSortArgs sa;
             sa.rho.explicit_rho = nullptr;
             if (j.rho) {
-                CU(cudaMemcpyAsync(d_rho, j.rho + e0 * o.fr_bytes, np * o.fr_bytes, cudaMemcpyHostToDevice, s));
+                const uint8_t* src = repack_scalars(o, j.rho + e0 * o.fr_bytes, np, keep);
+                CU(cudaMemcpyAsync(d_rho, src, np * scalar_stride(o), cudaMemcpyHostToDevice, s));
                 sa.rho.explicit_rho = reinterpret_cast<const uint32_t*>(d_rho);
             } else {
                 memcpy(sa.rho.key, j.seed, 32);

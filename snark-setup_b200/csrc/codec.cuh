@@ -56,6 +56,33 @@ struct FieldIO<Fp<P>> {
         for (int i = 0; i < P::N - 1; i++) w[i] = canon.l[i];
         w[P::N - 1] = canon.l[P::N - 1] | flags;
     }
+    // ---- byte-granular twins: field elements whose serialized size is not a multiple of 4 (MNT4/6-753: 95 bytes)
+    static constexpr int BYTES = (P::BITS + 7) / 8;
+    SS_HD static int stride(const uint32_t*) { return WORDS; }
+    SS_HD static int stride(const uint8_t*) { return BYTES; }
+    SS_HD static int load(const uint8_t* b, bool has_flags, Fp<P>& out, uint32_t& flags) {
+        Fp<P> raw;
+        for (int i = 0; i < P::N; i++) {
+            uint32_t w = 0;
+            for (int k = 0; k < 4; k++)
+                if (4 * i + k < BYTES) w |= (uint32_t)b[4 * i + k] << (8 * k);
+            raw.l[i] = w;
+        }
+        flags = 0;
+        if (has_flags) {
+            constexpr int TW = (BYTES - 1) / 4, TS = 8 * ((BYTES - 1) % 4);  // word / bit offset of the last byte
+            flags = ((raw.l[TW] >> TS) & 0xc0u) << 24;                       // same positions as the word-aligned form
+            raw.l[TW] &= ~(0xc0u << TS);
+            if (flags == 0xc0000000u) return ERR_UNEXPECTED_FLAGS;
+        }
+        if (raw_ge_mod<P>(raw.l)) return ERR_INVALID_DATA;
+        out = fp_to_mont(raw);
+        return ERR_OK;
+    }
+    SS_HD static void store(uint8_t* b, const Fp<P>& canon, uint32_t flags) {
+        for (int i = 0; i < BYTES; i++) b[i] = (uint8_t)(canon.l[i >> 2] >> (8 * (i & 3)));
+        b[BYTES - 1] |= (uint8_t)(flags >> 24);
+    }
     SS_HD static Fp<P> canonical(const Fp<P>& m) { return fp_from_mont(m); }
     // y > -y on canonical integers; `c` canonical
     SS_HD static bool is_negative(const Fp<P>& c) {
@@ -84,9 +111,56 @@ struct FieldIO<Fp2<P>> {
         B::store(w, canon.c0, 0);
         B::store(w + P::N, canon.c1, flags);
     }
+    static constexpr int BYTES = 2 * B::BYTES;
+    SS_HD static int stride(const uint32_t*) { return WORDS; }
+    SS_HD static int stride(const uint8_t*) { return BYTES; }
+    SS_HD static int load(const uint8_t* b, bool has_flags, Fp2<P>& out, uint32_t& flags) {
+        uint32_t f0;
+        flags = 0;
+        int e = B::load(b, false, out.c0, f0);
+        if (e) return e;
+        return B::load(b + B::BYTES, has_flags, out.c1, flags);
+    }
+    SS_HD static void store(uint8_t* b, const Fp2<P>& canon, uint32_t flags) {
+        B::store(b, canon.c0, 0);
+        B::store(b + B::BYTES, canon.c1, flags);
+    }
     SS_HD static Fp2<P> canonical(const Fp2<P>& m) { return Fp2<P>{fp_from_mont(m.c0), fp_from_mont(m.c1)}; }
     // lexicographic, c1 first (ark-ff QuadExtField Ord)
     SS_HD static bool is_negative(const Fp2<P>& c) {
+        if (!c.c1.is_zero()) return B::is_negative(c.c1);
+        return B::is_negative(c.c0);
+    }
+};
+
+template <class P>
+struct FieldIO<Fp3<P>> {
+    using B = FieldIO<Fp<P>>;
+    static constexpr int WORDS = 3 * P::N;
+    static constexpr int BYTES = 3 * B::BYTES;
+    SS_HD static int stride(const uint32_t*) { return WORDS; }
+    SS_HD static int stride(const uint8_t*) { return BYTES; }
+    template <class T>
+    SS_HD static int load(const T* w, bool has_flags, Fp3<P>& out, uint32_t& flags) {
+        uint32_t f0;
+        flags = 0;
+        const int st = B::stride(w);
+        int e = B::load(w, false, out.c0, f0);
+        if (e) return e;
+        if ((e = B::load(w + st, false, out.c1, f0))) return e;
+        return B::load(w + 2 * st, has_flags, out.c2, flags);
+    }
+    template <class T>
+    SS_HD static void store(T* w, const Fp3<P>& canon, uint32_t flags) {
+        const int st = B::stride((const T*)w);
+        B::store(w, canon.c0, 0);
+        B::store(w + st, canon.c1, 0);
+        B::store(w + 2 * st, canon.c2, flags);
+    }
+    SS_HD static Fp3<P> canonical(const Fp3<P>& m) { return Fp3<P>{fp_from_mont(m.c0), fp_from_mont(m.c1), fp_from_mont(m.c2)}; }
+    // lexicographic, c2 first, then c1, then c0 (ark-ff CubicExtField Ord)
+    SS_HD static bool is_negative(const Fp3<P>& c) {
+        if (!c.c2.is_zero()) return B::is_negative(c.c2);
         if (!c.c1.is_zero()) return B::is_negative(c.c1);
         return B::is_negative(c.c0);
     }
@@ -203,8 +277,8 @@ SS_HD bool in_subgroup(const Affine<typename G::F>& p) {
 }
 
 // Decode one element.  Returns ERR_*; `out` is valid when ERR_OK.
-template <class G>
-SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typename G::F>& out) {
+template <class G, class T>
+SS_HD int decode_point(const T* w, bool compressed, int check, Affine<typename G::F>& out) {
     using F = typename G::F;
     using IO = FieldIO<F>;
     uint32_t flags;
@@ -215,7 +289,7 @@ SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typ
         if (flags & FLAG_INF_W) {
             out.inf = true;
         } else {
-            F rhs = fp_add(fp_mul(fp_sqr(out.x), out.x), G::b());
+            F rhs = curve_rhs(out.x, G::b());
             F y;
             if (!fp_sqrt_any(rhs, y)) return ERR_INVALID_DATA;
             bool neg = IO::is_negative(IO::canonical(y));
@@ -225,7 +299,7 @@ SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typ
     } else {
         uint32_t fx;
         if ((e = IO::load(w, false, out.x, fx)) != ERR_OK) return e;
-        if ((e = IO::load(w + IO::WORDS, true, out.y, flags)) != ERR_OK) return e;
+        if ((e = IO::load(w + IO::stride(w), true, out.y, flags)) != ERR_OK) return e;
         if (flags & FLAG_INF_W) out.inf = true;
     }
     if (out.inf) {
@@ -240,14 +314,14 @@ SS_HD int decode_point(const uint32_t* w, bool compressed, int check, Affine<typ
 }
 
 // Encode one affine element (Montgomery coordinates) to `w`.
-template <class G>
-SS_HD void encode_point(uint32_t* w, bool compressed, const Affine<typename G::F>& p) {
+template <class G, class T>
+SS_HD void encode_point(T* w, bool compressed, const Affine<typename G::F>& p) {
     using F = typename G::F;
     using IO = FieldIO<F>;
     if (p.inf) {
-        const int words = compressed ? IO::WORDS : 2 * IO::WORDS;
+        const int words = (compressed ? 1 : 2) * IO::stride((const T*)w);
         for (int i = 0; i < words - 1; i++) w[i] = 0;
-        w[words - 1] = FLAG_INF_W;
+        w[words - 1] = (T)(FLAG_INF_W >> (8 * (4 - (int)sizeof(T))));  // 0x40 in the last byte
         return;
     }
     F xc = IO::canonical(p.x);
@@ -257,7 +331,7 @@ SS_HD void encode_point(uint32_t* w, bool compressed, const Affine<typename G::F
         IO::store(w, xc, flags);
     } else {
         IO::store(w, xc, 0);
-        IO::store(w + IO::WORDS, yc, flags);
+        IO::store(w + IO::stride((const T*)w), yc, flags);
     }
 }
 

@@ -34,6 +34,7 @@ struct Bls377G1 {
     static constexpr int COORD_LIMBS = 12;
     static constexpr int USIZE = 96, CSIZE = 48;
     static constexpr int SMUL_MINB = 4;  // k_scalar_mul blocks/SM: 128 regs, 16 warps/SM measured best (A/B in profiles/)
+    static constexpr bool HAS_ENDO = true, BYTE_IO = false;
     static const char* name() { return "bls12_377.g1"; }
     SS_HD static F b() {
         F r;
@@ -59,6 +60,7 @@ struct Bls377G2 {
     using GP = Bls377G2Params;
     static constexpr int USIZE = 192, CSIZE = 96;
     static constexpr int SMUL_MINB = 1;  // Fq2 needs the full 255 registers
+    static constexpr bool HAS_ENDO = true, BYTE_IO = false;
     static const char* name() { return "bls12_377.g2"; }
     SS_HD static F b() {
         F r;
@@ -97,6 +99,7 @@ struct Bls377G2L {
 #define SS_G2L_MINB 3
 #endif
     static constexpr int SMUL_MINB = SS_G2L_MINB;  // 128-thread blocks per SM (168 registers at 3)
+    static constexpr bool HAS_ENDO = true, BYTE_IO = false;
     static const char* name() { return "bls12_377.g2"; }
     SS_HD static F b() {
         F r;
@@ -123,6 +126,7 @@ struct Bw6Group {
     using GP = GPx;
     static constexpr int USIZE = 192, CSIZE = 96;
     static constexpr int SMUL_MINB = 1;
+    static constexpr bool HAS_ENDO = true, BYTE_IO = false;
     static const char* name() { return GP::b(0) == Bw6G1Params::b(0) ? "bw6_761.g1" : "bw6_761.g2"; }
     SS_HD static F b() {
         F r;
@@ -144,6 +148,96 @@ struct Bw6Group {
 using Bw6G1 = Bw6Group<Bw6G1Params>;
 using Bw6G2 = Bw6Group<Bw6G2Params>;
 
+// ---- MNT4-753 / MNT6-753 (setup-utils/src/converters.rs:18-45): y^2 = x^3 + a x + b with a != 0 ------------------------
+// G1 has prime order (cofactor 1); G2 lives on the twist over Fq2 (MNT4) / Fq3 (MNT6).  Field elements serialize to 95
+// bytes, so elements are NOT word-aligned in the reference's packed layout (BYTE_IO); no efficient endomorphism is
+// used (HAS_ENDO = false: plain double-and-add).  Constants: tools/gen_constants.py from oracle/pyref.py, where they are
+// verified (curve orders, twist orders, non-residues).  The arkworks G2 GENERATOR constants are not known here.
+template <class GPx, class FqP, class FrP, int WHICH>
+struct MntG1 {
+    using F = Fp<FqP>;
+    using Fr = Fp<FrP>;
+    using GP = GPx;
+    static constexpr int USIZE = 190, CSIZE = 95;
+    static constexpr int SMUL_MINB = 1;
+    static constexpr bool HAS_ENDO = false, BYTE_IO = true, HAS_GENERATOR = true;
+    static const char* name() { return WHICH == 4 ? "mnt4_753.g1" : "mnt6_753.g1"; }
+    SS_HD static F a() { F r; for (int i = 0; i < 24; i++) r.l[i] = GP::a(i); return r; }
+    SS_HD static F b() { F r; for (int i = 0; i < 24; i++) r.l[i] = GP::b(i); return r; }
+    SS_HD static Affine<F> generator() {
+        Affine<F> g;
+        for (int i = 0; i < 24; i++) {
+            g.x.l[i] = GP::gx(i);
+            g.y.l[i] = GP::gy(i);
+        }
+        g.inf = false;
+        return g;
+    }
+};
+using Mnt4G1 = MntG1<Mnt4G1Params, Mnt753Q, Mnt753R, 4>;
+using Mnt6G1 = MntG1<Mnt6G1Params, Mnt753R, Mnt753Q, 6>;
+
+struct Mnt4G2 {
+    using F = Fp2<Mnt753Q>;
+    using Fr = Fp<Mnt753R>;
+    using GP = Mnt4G2Params;
+    static constexpr int USIZE = 380, CSIZE = 190;
+    static constexpr int SMUL_MINB = 1;
+    static constexpr bool HAS_ENDO = false, BYTE_IO = true, HAS_GENERATOR = false;
+    static const char* name() { return "mnt4_753.g2"; }
+    SS_HD static F a() { F r; for (int i = 0; i < 24; i++) { r.c0.l[i] = GP::a_c0(i); r.c1.l[i] = GP::a_c1(i); } return r; }
+    SS_HD static F b() { F r; for (int i = 0; i < 24; i++) { r.c0.l[i] = GP::b_c0(i); r.c1.l[i] = GP::b_c1(i); } return r; }
+    SS_HD static Affine<F> generator() { return Affine<F>{F::zero(), F::zero(), true}; }
+};
+struct Mnt6G2 {
+    using F = Fp3<Mnt753R>;
+    using Fr = Fp<Mnt753Q>;
+    using GP = Mnt6G2Params;
+    static constexpr int USIZE = 570, CSIZE = 285;
+    static constexpr int SMUL_MINB = 1;
+    static constexpr bool HAS_ENDO = false, BYTE_IO = true, HAS_GENERATOR = false;
+    static const char* name() { return "mnt6_753.g2"; }
+    SS_HD static F a() {
+        F r;
+        for (int i = 0; i < 24; i++) { r.c0.l[i] = GP::a_c0(i); r.c1.l[i] = GP::a_c1(i); r.c2.l[i] = GP::a_c2(i); }
+        return r;
+    }
+    SS_HD static F b() {
+        F r;
+        for (int i = 0; i < 24; i++) { r.c0.l[i] = GP::b_c0(i); r.c1.l[i] = GP::b_c1(i); r.c2.l[i] = GP::b_c2(i); }
+        return r;
+    }
+    SS_HD static Affine<F> generator() { return Affine<F>{F::zero(), F::zero(), true}; }
+};
+
+// The curve coefficient a, keyed by the COORDINATE FIELD type (every field below belongs to exactly one group, so the
+// formula templates — which only know F — can ask for it): zero for the BLS12-377 / BW6-761 fields.
+template <class F>
+struct CurveCoeffA {
+    static constexpr bool ZERO = true;
+    SS_HD static F a() { return F::zero(); }
+};
+template <>
+struct CurveCoeffA<Fp<Mnt753Q>> {
+    static constexpr bool ZERO = false;
+    SS_HD static Fp<Mnt753Q> a() { return Mnt4G1::a(); }
+};
+template <>
+struct CurveCoeffA<Fp<Mnt753R>> {
+    static constexpr bool ZERO = false;
+    SS_HD static Fp<Mnt753R> a() { return Mnt6G1::a(); }
+};
+template <>
+struct CurveCoeffA<Fp2<Mnt753Q>> {
+    static constexpr bool ZERO = false;
+    SS_HD static Fp2<Mnt753Q> a() { return Mnt4G2::a(); }
+};
+template <>
+struct CurveCoeffA<Fp3<Mnt753R>> {
+    static constexpr bool ZERO = false;
+    SS_HD static Fp3<Mnt753R> a() { return Mnt6G2::a(); }
+};
+
 // ---- formulas ---------------------------------------------------------------------------------
 // Group operations come in three flavours: *_inl (the formula), *_call (one out-of-line copy per
 // field, used for the wide fields where inlining every Fp2 / 24-limb add-sub chain makes the NVVM
@@ -155,6 +249,18 @@ SS_HD Jac<F> jac_dbl_cold(const Jac<F>& p);
 template <class F>
 SS_HD Jac<F> jac_dbl_inl(const Jac<F>& p) {
     if (p.Z.is_zero()) return p;
+    if constexpr (!CurveCoeffA<F>::ZERO) {
+        // dbl-2007-bl (general a): 1M + 8S + 1 multiplication by a
+        F XX = fp_sqr(p.X), YY = fp_sqr(p.Y), ZZ = fp_sqr(p.Z);
+        F YYYY = fp_sqr(YY);
+        F S = fp_dbl(fp_sub(fp_sub(fp_sqr(fp_add(p.X, YY)), XX), YYYY));
+        F M = fp_add(fp_add(fp_dbl(XX), XX), fp_mul(CurveCoeffA<F>::a(), fp_sqr(ZZ)));
+        Jac<F> r;
+        r.X = fp_sub(fp_sqr(M), fp_dbl(S));
+        r.Y = fp_sub(fp_mul(M, fp_sub(S, r.X)), fp_dbl(fp_dbl(fp_dbl(YYYY))));
+        r.Z = fp_sub(fp_sub(fp_sqr(fp_add(p.Y, p.Z)), YY), ZZ);
+        return r;
+    }
     F A = fp_sqr(p.X);
     F B = fp_sqr(p.Y);
     F C = fp_sqr(B);
@@ -400,10 +506,16 @@ SS_HD Affine<F> affine_neg(const Affine<F>& p) {
     return Affine<F>{p.x, fp_neg(p.y), p.inf};
 }
 
+// x^3 + a x + b
+template <class F>
+SS_HD F curve_rhs(const F& x, const F& b) {
+    if constexpr (!CurveCoeffA<F>::ZERO) return fp_add(fp_mul(fp_add(fp_sqr(x), CurveCoeffA<F>::a()), x), b);
+    else return fp_add(fp_mul(fp_sqr(x), x), b);
+}
 template <class F>
 SS_HD bool on_curve(const Affine<F>& p, const F& b) {
     if (p.inf) return true;
-    return fp_sqr(p.y) == fp_add(fp_mul(fp_sqr(p.x), p.x), b);
+    return fp_sqr(p.y) == curve_rhs(p.x, b);
 }
 
 // MSB-first double-and-add over `nbits` bits of a little-endian limb array (the reference

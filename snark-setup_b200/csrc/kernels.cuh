@@ -84,6 +84,41 @@ struct FieldWords<Fp2<P>> {
     }
 };
 
+template <class P>
+struct FieldWords<Fp3<P>> {
+    static constexpr int W = 3 * P::N;
+    using B = FieldWords<Fp<P>>;
+    SS_D static void store(uint32_t* base, uint64_t stride, const Fp3<P>& a) {
+        B::store(base, stride, a.c0);
+        B::store(base + P::N * stride, stride, a.c1);
+        B::store(base + 2 * P::N * stride, stride, a.c2);
+    }
+    SS_D static Fp3<P> load(const uint32_t* base, uint64_t stride) {
+        return Fp3<P>{B::load(base, stride), B::load(base + P::N * stride, stride), B::load(base + 2 * P::N * stride, stride)};
+    }
+    SS_D static Fp3<P> unpack(const uint32_t* w) { return Fp3<P>{B::unpack(w), B::unpack(w + P::N), B::unpack(w + 2 * P::N)}; }
+    SS_D static void pack(uint32_t* w, const Fp3<P>& a) {
+        B::pack(w, a.c0);
+        B::pack(w + P::N, a.c1);
+        B::pack(w + 2 * P::N, a.c2);
+    }
+};
+
+// serialized element i of a packed buffer: word-aligned for the ceremony curves, byte-granular for the MNT curves
+// (95-byte field elements), see G::BYTE_IO in ec.cuh
+template <class G>
+SS_D int decode_at(const uint32_t* base, uint64_t i, bool compressed, int check, Affine<typename G::F>& p) {
+    const int sz = compressed ? G::CSIZE : G::USIZE;
+    if constexpr (G::BYTE_IO) return decode_point<G>(reinterpret_cast<const uint8_t*>(base) + i * sz, compressed, check, p);
+    else return decode_point<G>(base + i * (sz / 4), compressed, check, p);
+}
+template <class G>
+SS_D void encode_at(uint32_t* base, uint64_t i, bool compressed, const Affine<typename G::F>& p) {
+    const int sz = compressed ? G::CSIZE : G::USIZE;
+    if constexpr (G::BYTE_IO) encode_point<G>(reinterpret_cast<uint8_t*>(base) + i * sz, compressed, p);
+    else encode_point<G>(base + i * (sz / 4), compressed, p);
+}
+
 // ---- scalar preparation -------------------------------------------------------------------------
 // tab[j] = tau^(2^j) (Montgomery), j < 64; coeff_m = coeff (Montgomery) or 1.
 template <class FrP>
@@ -202,9 +237,8 @@ __global__ void __launch_bounds__(128, (G::F::CALL_GROUP_OPS ? 1 : SS_DECODE_MIN
     using FW = FieldWords<F>;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const int ewords = (a.in_compressed ? G::CSIZE : G::USIZE) / 4;
     Affine<F> p;
-    int e = decode_point<G>(a.in + i * ewords, a.in_compressed != 0, a.check, p);
+    int e = decode_at<G>(a.in, i, a.in_compressed != 0, a.check, p);
     if (e != ERR_OK) {
         report(a.status, i, e);
         p.inf = true;
@@ -313,10 +347,12 @@ __global__ void __launch_bounds__(SS_SMUL_TPB, G::SMUL_MINB) k_scalar_mul(Scalar
         }
         s = fp_from_mont(s);
     }
+    Jac<F> r;
 #if defined(SS_SCALAR_MUL_LADDER)
-    Jac<F> r = jac_mul_bits<F>(base, [&](int k) { return s.l[k]; }, FrP::BITS);  // reference algorithm (A/B)
+    r = jac_mul_bits<F>(base, [&](int k) { return s.l[k]; }, FrP::BITS);  // reference algorithm (A/B)
 #else
-    Jac<F> r = scalar_mul_endo<G>(base, s.l, a.plain_ladder != 0);  // GLV / GLS + signed windows + common-Z table (glv.cuh)
+    if constexpr (G::HAS_ENDO) r = scalar_mul_endo<G>(base, s.l, a.plain_ladder != 0);  // GLV / GLS + signed windows + common-Z table (glv.cuh)
+    else r = jac_mul_ladder_cold<G>(base, s.l);  // MNT curves: no endomorphism, the reference's double-and-add
 #endif
     uint32_t* o = a.jac + i;
     FW::store(o, a.n, r.X);
@@ -435,7 +471,6 @@ __global__ void __launch_bounds__(128) k_normalize_encode(NormalizeArgs a) {
         last = e;
     }
     F inv = fp_inv(acc);
-    const int owords = (a.out_compressed ? G::CSIZE : G::USIZE) / 4;
     for (uint64_t e = last;; e -= T) {
         F z = FW::load(Zb + e, n);
         Affine<F> p;
@@ -456,7 +491,7 @@ __global__ void __launch_bounds__(128) k_normalize_encode(NormalizeArgs a) {
             store_affine<G>(a.aff_out, e, p);
             a.inf_out[e] = p.inf ? 1 : 0;
         } else {
-            encode_point<G>(a.out + e * owords, a.out_compressed != 0, p);
+            encode_at<G>(a.out, e, a.out_compressed != 0, p);
         }
         if (e < T) break;
     }
@@ -476,9 +511,8 @@ template <class G>
 __global__ void __launch_bounds__(128) k_encode(EncodeArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.count) return;
-    const int ow = (a.out_compressed ? G::CSIZE : G::USIZE) / 4;
     Affine<typename G::F> p = load_affine<G>(a.aff, a.inf, a.n, i);
-    encode_point<G>(a.out + i * ow, a.out_compressed != 0, p);
+    encode_at<G>(a.out, i, a.out_compressed != 0, p);
 }
 
 // ---- p.mul_bigint(r).is_zero() for every element (setup-utils/src/elements.rs:138-142) -----------
@@ -565,7 +599,7 @@ __global__ void k_sum_points(const uint32_t* pts, int count, uint32_t* out, unsi
     Jac<F> acc = Jac<F>::identity();
     for (int i = 0; i < count; i++) {
         Affine<F> p;
-        int e = decode_point<G>(pts + (size_t)i * (G::USIZE / 4), false, CHECK_NO, p);
+        int e = decode_at<G>(pts, (uint64_t)i, false, CHECK_NO, p);
         if (e != ERR_OK) {
             report(status, i, e);
             return;
@@ -580,14 +614,14 @@ __global__ void k_sum_points(const uint32_t* pts, int count, uint32_t* out, unsi
     } else {
         r = jac_to_affine_with_zinv(acc, fp_inv(acc.Z));
     }
-    encode_point<G>(out, false, r);
+    encode_at<G>(out, 0, false, r);
 }
 
 // ---- init_element (setup-utils/src/io/write.rs:45-55): the serialized group generator --------------------------
 template <class G>
 __global__ void k_generator(uint32_t* out, int compressed) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    encode_point<G>(out, compressed != 0, G::generator());
+    encode_at<G>(out, 0, compressed != 0, G::generator());
 }
 
 // ---- function table seen by api.cu -------------------------------------------------------------
@@ -596,6 +630,8 @@ struct GroupOps {
     int usize, csize;      // serialized element sizes
     int fr_words;          // scalar limbs (u32)
     int fr_bytes;          // canonical scalar bytes
+    int fr_bits;           // scalar field size in bits
+    int has_generator;     // 0: the reference's generator constant of this group is not known (MNT G2)
     int coord_words;       // FW
     void (*prepare_scalars)(const uint32_t* tau_le, const uint32_t* coeff_le, uint32_t* tab, uint32_t* coeff_m,
                             cudaStream_t);
@@ -609,6 +645,11 @@ struct GroupOps {
     void (*sum_points)(const uint32_t* pts, int count, uint32_t* out, unsigned long long* status, cudaStream_t);
     void (*generator)(uint32_t* out, int compressed, cudaStream_t);
 };
+
+template <class G, class = void>
+struct HasGenerator : std::true_type {};
+template <class G>
+struct HasGenerator<G, std::enable_if_t<!G::HAS_GENERATOR>> : std::false_type {};
 
 template <class G>
 struct GroupLaunch {
@@ -683,6 +724,8 @@ struct GroupLaunch {
         o.csize = G::CSIZE;
         o.fr_words = FrP::N;
         o.fr_bytes = (FrP::BITS + 7) / 8;
+        o.fr_bits = FrP::BITS;
+        o.has_generator = HasGenerator<G>::value ? 1 : 0;
         o.coord_words = FieldWords<typename G::F>::W;
         o.prepare_scalars = &prepare_scalars;
         o.powers = &powers;
@@ -702,5 +745,9 @@ const GroupOps& ops_bls377_g1();
 const GroupOps& ops_bls377_g2();
 const GroupOps& ops_bw6_g1();
 const GroupOps& ops_bw6_g2();
+const GroupOps& ops_mnt4_g1();
+const GroupOps& ops_mnt4_g2();
+const GroupOps& ops_mnt6_g1();
+const GroupOps& ops_mnt6_g2();
 
 }  // namespace ss

@@ -64,7 +64,7 @@ SS_D uint32_t rho_digit(const RhoSource& r, const uint32_t* words, int w, int c)
     return d;
 }
 
-SS_D void rho_load(const RhoSource& r, uint64_t i, uint32_t* words /*[12]*/) {
+SS_D void rho_load(const RhoSource& r, uint64_t i, uint32_t* words /*[24]*/) {
     if (r.explicit_rho) {
         for (int k = 0; k < r.frw; k++) words[k] = r.explicit_rho[i * r.frw + k];
     } else {
@@ -86,7 +86,7 @@ struct MsmSortArgs {
 static __global__ void k_msm_hist(MsmSortArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    uint32_t words[12];
+    uint32_t words[24];
     rho_load(a.rho, i, words);
     const uint32_t B = 1u << a.c;
     for (int w = 0; w < a.W; w++) {
@@ -130,7 +130,7 @@ static __global__ void k_msm_scan(uint32_t* hist, uint32_t* cursor, uint32_t* co
 static __global__ void k_msm_scatter(MsmSortArgs a) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    uint32_t words[12];
+    uint32_t words[24];
     rho_load(a.rho, i, words);
     const uint32_t B = 1u << a.c;
     for (int w = 0; w < a.W; w++) {
@@ -468,5 +468,9 @@ const MsmOps& msm_ops_bls377_g1();
 const MsmOps& msm_ops_bls377_g2();
 const MsmOps& msm_ops_bw6_g1();
 const MsmOps& msm_ops_bw6_g2();
+const MsmOps& msm_ops_mnt4_g1();
+const MsmOps& msm_ops_mnt4_g2();
+const MsmOps& msm_ops_mnt6_g1();
+const MsmOps& msm_ops_mnt6_g2();
 
 }  // namespace ss

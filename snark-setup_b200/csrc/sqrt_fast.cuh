@@ -194,6 +194,11 @@ SS_HD bool fp_sqrt_any(const Fp<P>& a, Fp<P>& out) {
     return fp_sqrt(a, out);
 }
 SS_HD bool fp_sqrt_any(const FqB& a, FqB& out) { return fp_sqrt_fast(a, out); }
+// MNT4-753 G2 (Fq2 = Fq[u]/(u^2 - 13)): generic norm method; MNT6-753 G2 (Fq3): Tonelli-Shanks in Fq3*
+SS_HD bool fp_sqrt_any(const Fp2<Mnt753Q>& a, Fp2<Mnt753Q>& out) { return fp_sqrt(a, out) && fp_sqr(out) == a; }
+SS_HD bool fp_sqrt_any(const Fp3<Mnt753R>& a, Fp3<Mnt753R>& out) {
+    return fp3_sqrt<Mnt753R, Mnt6Fq3Sqrt>(a, out) && fp_sqr(out) == a;
+}
 SS_HD bool fp_sqrt_any(const Fp2<Bls377Fq>& a, Fp2<Bls377Fq>& out) { return fp2_sqrt_fast(a, out); }
 
 }  // namespace ss

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 lib_path = os.environ.get("SS_LIB") or os.path.join(_CSRC, "libsnarksetup_b200.so")  # SS_LIB: A/B kernel variants
 
-BLS12_377, BW6_761 = 0, 1
+BLS12_377, BW6_761, MNT4_753, MNT6_753 = 0, 1, 2, 3
 G1, G2 = 0, 1
 CHECK_FULL, CHECK_ONLY_NON_ZERO, CHECK_ONLY_IN_GROUP, CHECK_NO = 0, 1, 2, 3
 SUBGROUP_AUTO, SUBGROUP_DIRECT, SUBGROUP_BATCHED, SUBGROUP_NO = 0, 1, 2, 3

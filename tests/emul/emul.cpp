@@ -184,6 +184,44 @@ static int count_scalar_mul(const uint8_t* in, const uint8_t* scalar, unsigned l
     return r.is_identity() ? 1 : 0;
 }
 
+// ---- MNT4/6-753 (a != 0, Fq2 / Fq3 twists, byte-granular codec): point arithmetic through the device headers --------
+// op 0: transcode (decode with `check`, re-encode)   op 1: scalar multiplication by the 95-byte canonical scalar
+// op 2: P + Q through jac_madd (first operand given a non-trivial Z)   op 3: r * P == O ? (returns 1 / 0)
+template <class G>
+static int mnt_op(int op, const uint8_t* in, int in_c, int check, const uint8_t* arg, uint8_t* out, int out_c) {
+    using F = typename G::F;
+    Affine<F> p;
+    int e = decode_point<G>(in, in_c != 0, check, p);
+    if (e) return -e;
+    Jac<F> r = p.inf ? Jac<F>::identity() : Jac<F>{p.x, p.y, F::one()};
+    if (op == 1) {
+        uint32_t k[24] = {0};
+        memcpy(k, arg, 95);
+        r = jac_mul_bits<F>(p, [&](int i) { return k[i]; }, 753);
+    } else if (op == 2) {
+        Affine<F> q;
+        if ((e = decode_point<G>(arg, false, CHECK_NO, q))) return -e;
+        if (!p.inf) {
+            F two = fp_dbl(F::one());
+            r.X = fp_mul(p.x, fp_sqr(two));
+            r.Y = fp_mul(p.y, fp_mul(fp_sqr(two), two));
+            r.Z = two;
+        }
+        r = jac_madd(r, q);
+    } else if (op == 3) {
+        return in_subgroup_rmul<G>(p) ? 1 : 0;
+    }
+    Affine<F> a;
+    if (r.is_identity()) {
+        a.inf = true;
+        a.x = F::zero();
+        a.y = F::zero();
+    } else {
+        a = jac_to_affine_with_zinv(r, fp_inv(r.Z));
+    }
+    encode_point<G>(out, out_c != 0, a);
+    return 0;
+}
 extern "C" {
 // counts[kind][limbs] (kind 0 = multiplications, 1 = squarings) executed by ONE scalar_mul_endo<G> (glv.cuh)
 int emul_count_scalar_mul(int group, const uint8_t* in, const uint8_t* scalar, unsigned long long* counts) {
@@ -283,5 +321,15 @@ int emul_fp2l_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     store_raw<P>(out, fp_from_mont(r0));
     store_raw<P>(out + 48, fp_from_mont(r1));
     return 0;
+}
+
+int emul_mnt_op(int group, int op, const uint8_t* in, int in_c, int check, const uint8_t* arg, uint8_t* out, int out_c) {
+    switch (group) {
+        case 0: return mnt_op<Mnt4G1>(op, in, in_c, check, arg, out, out_c);
+        case 1: return mnt_op<Mnt4G2>(op, in, in_c, check, arg, out, out_c);
+        case 2: return mnt_op<Mnt6G1>(op, in, in_c, check, arg, out, out_c);
+        case 3: return mnt_op<Mnt6G2>(op, in, in_c, check, arg, out, out_c);
+    }
+    return -100;
 }
 }
