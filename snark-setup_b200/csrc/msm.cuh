@@ -390,7 +390,7 @@ __global__ void k_msm_reduce3(MsmReduceArgs a) {
     } else {
         p = jac_to_affine_with_zinv(r, fp_inv(r.Z));
     }
-    encode_point<G>(which == 0 ? a.out_s : a.out_sx, false, p);
+    encode_at<G>(which == 0 ? a.out_s : a.out_sx, 0, false, p);
 }
 
 // ---- launchers ----------------------------------------------------------------------------------
