@@ -180,7 +180,7 @@ static int count_scalar_mul(const uint8_t* in, const uint8_t* scalar, unsigned l
     memcpy(k, scalar, 4 * G::Fr::N);
     memset(ss_op_count, 0, sizeof(ss_op_count));
     Jac<F> r = scalar_mul_endo<G>(p, k);
-    memcpy(counts, ss_op_count, sizeof(ss_op_count));
+    memcpy(counts, ss_op_count, 2 * 32 * sizeof(unsigned long long));  // [0] multiplications, [1] squarings (the caller holds 2 x 32 counters)
     return r.is_identity() ? 1 : 0;
 }
 
