@@ -57,7 +57,11 @@ struct Bls377Pairing {
     static constexpr int XPOS = 2;               // D-type: x_Q = x' w^2, y_Q = y' w^3
     static constexpr bool XI_ON_CONST = false;
     static constexpr bool ATE = true;            // Miller loop over u on the twist (64 bits) instead of r on G1 (253)
-    static constexpr bool FROB4 = true;          // hard part as a 4-way simultaneous exponentiation over f^(q^i)
+#if defined(SS_PAIRING_FROB4)
+    static constexpr bool UCHAIN = false, FROB4 = true;  // A/B: the round-1 hard part (4-way simultaneous exponentiation)
+#else
+    static constexpr bool UCHAIN = true, FROB4 = false;  // hard part along the u-chain, see k_same_ratio
+#endif
     static constexpr bool FROB2 = false;
     SS_D static F mul_xi(const F& a) { return F{fp_neg(fp_mul5(a.c1)), a.c0}; }  // xi = u, u^2 = -5
 };
@@ -70,7 +74,7 @@ struct Bw6Pairing {
     static constexpr int XPOS = 4;               // M-type: xi x_Q = x' w^4, xi y_Q = y' w^3 (whole line scaled by xi)
     static constexpr bool XI_ON_CONST = true;
     static constexpr bool ATE = false;
-    static constexpr bool FROB4 = false;
+    static constexpr bool UCHAIN = false, FROB4 = false;
     static constexpr bool FROB2 = true;  // hard part as f^a0 * (f^q)^a1 with the Gauss-reduced (a0, a1), 572 bits
     SS_D static F mul_xi(const F& a) { return fp_neg(fp_dbl(fp_dbl(a))); }  // xi = -4
 };
@@ -294,7 +298,29 @@ __global__ void __launch_bounds__(32) k_same_ratio(const uint32_t* g1_pairs, con
     for (int i = 0; i < Fq::N; i++) z.l[i] = PP::frob(k, i);
     F f2 = ext_mul<C>(fscale(f1, z), f1, k);  // f1^(Q + 1): (sum c_k w^k)^Q = sum c_k zeta^k w^k
     F acc;
-    if constexpr (C::FROB4) {
+    if constexpr (C::UCHAIN) {
+        // BLS12 hard part along the seed (Hayashida-Hayasaka-Teruya):  3 (q^4 - q^2 + 1)/r = (u-1)^2 (u+q) (u^2+q^2-1) + 3
+        // (checked numerically for BLS12-377 in tools/gen_constants.py), i.e. five exponentiations by the 64-bit, weight-7
+        // seed u — 315 squarings + 30 multiplications instead of the 314 + 295 of the 4-way simultaneous form.  f2 lies in
+        // the cyclotomic subgroup, where x^-1 = x^(q^6) (w -> -w); the value obtained is f2^(3 hard), and gcd(3, r) = 1,
+        // so "== 1" is the same verdict.
+        auto inv = [&](const F& x) { return (k & 1) ? fp_neg(x) : x; };
+        auto exp_u = [&](const F& x) {
+            F r = x;
+#pragma unroll 1
+            for (int i = PP::ATE_BITS - 2; i >= 0; i--) {
+                r = ext_mul<C>(r, r, k);
+                if ((PP::ate(i >> 5) >> (i & 31)) & 1) r = ext_mul<C>(r, x, k);
+            }
+            return r;
+        };
+        F a = ext_mul<C>(exp_u(f2), inv(f2), k);                                  // f2^(u-1)
+        a = ext_mul<C>(exp_u(a), inv(a), k);                                      // ^(u-1)
+        F b2 = ext_mul<C>(exp_u(a), frobenius_q<C>(a, k), k);                     // ^(u+q)
+        F c = ext_mul<C>(exp_u(exp_u(b2)), frobenius_q<C>(frobenius_q<C>(b2, k), k), k);
+        c = ext_mul<C>(c, inv(b2), k);                                            // ^(u^2+q^2-1)
+        acc = ext_mul<C>(c, ext_mul<C>(ext_mul<C>(f2, f2, k), f2, k), k);         // * f2^3
+    } else if constexpr (C::FROB4) {
         // hard = sum_i h_i q^i (i < 4): f2^hard = prod_i (f2^(q^i))^(h_i), one squaring and at most one table
         // multiplication per bit of the (<= 314-bit) digits; tab[m] = prod_{i in m} f2^(q^i)
         F tab[16];
