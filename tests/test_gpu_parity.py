@@ -197,6 +197,45 @@ def test_phase1_marlin(mode, chunk_index, chunk_size):
     assert bytes(newc[64:]) == bytes(R.phase1_computation(rp, bytes(acc), False, False, R.NO, tau, alpha, 0))[64:]
 
 
+def test_config_c1_complete_transcript_with_public_key():
+    """BASELINE.json configs[0] as a TRANSCRIPT: keys from seeds (oracle/pyref_host.py restates derive_rng_from_seed /
+    key_generation / hash_to_g2 — recalled, see its header), new -> contribute -> verify at power 10 with the compressed
+    PublicKey appended to the response (public_key.rs:40-55, contribute.rs:135-137); the COMPLETE response file hashes
+    to the oracle's, the proofs of knowledge verify (verification.rs:83-133) and the four ratio checks pass on the
+    device."""
+    import hashlib
+    import coracle as O
+    import pyref_host as H
+    cv, cid = R.BLS12_377, S.BLS12_377
+    rp, sp = R.Phase1Parameters(cv, 10, 256), S.Phase1Parameters(cid, 10, 256)
+    blank = bytearray(S.phase1_initialization(sp, False))
+    blank[:64] = hashlib.blake2b(b"").digest()                      # blank_hash (helpers.rs:392-394)
+    assert bytes(blank[64:]) == bytes(R.phase1_initialization(rp, False))[64:]
+    digest = hashlib.blake2b(bytes(blank)).digest()                 # calculate_hash of the challenge
+    pk, keys = H.key_generation(cv, H.derive_rng_from_seed(b"c1-contributor-1"), digest)
+    resp = bytearray(sp.contribution_size)
+    resp[:64] = digest                                              # the response starts with the challenge hash
+    S.phase1_computation(sp, bytes(blank), memoryview(resp)[:sp.get_length(True)], False, True, S.CHECK_NO, *keys)
+    resp[sp.contribution_size - sp.public_key_size:] = H.public_key_bytes(cv, pk)
+    want = bytearray(rp.contribution_size)
+    body = O.phase1_computation(0, bytes(blank), rp.get_length(True), False, True, 3, rp.g1_chunk_size, rp.other_chunk_size,
+                                0, *keys)
+    want[:len(body)] = body
+    want[:64] = digest
+    want[rp.contribution_size - rp.public_key_size:] = H.public_key_bytes(cv, pk)
+    assert hashlib.blake2b(bytes(resp)).digest() == hashlib.blake2b(bytes(want)).digest()   # the .hash file of the response
+    # verification: proofs of knowledge (host, oracle pairing) + the vectors and their four ratio verdicts (device)
+    assert H.verify_proofs_of_knowledge(cv, pk, digest)
+    newc = bytearray(sp.get_length(False))
+    S.phase1_verification_ratios(sp, bytes(resp[:sp.get_length(True)]), True, newc, False, seed=bytes(range(32)))
+    assert bytes(newc[64:]) == O.phase1_computation(0, bytes(blank), rp.get_length(False), False, False, 3, rp.g1_chunk_size,
+                                                    rp.other_chunk_size, 0, *keys)[64:]
+    # first-element checks of verification.rs:136-213: tau_g1[1] = tau * G1 etc. against the public key
+    offs = rp.split_offsets(False)
+    tau_g1_1 = cv.g1.decode(bytes(newc[offs[0][0] + 96:offs[0][0] + 192]), False)
+    assert R.same_ratio(cv, (cv.g1.gen, tau_g1_1), (H.compute_g2_s(cv, H.bls12_377_g2_cofactor(), digest, *pk["tau_g1"], 0), pk["tau_g2"]))
+
+
 def test_config_c1_bls12_377_power10_batch256():
     """BASELINE.json configs[0]: new + contribute + verify at power 10, batch 256 — the whole response and the
     whole new challenge byte for byte against the C++ oracle, plus the BLAKE2b-512 digests a CLI run would

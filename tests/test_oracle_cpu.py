@@ -142,3 +142,35 @@ def test_oracles_agree_random_and_errors(cid, cv, gid, g):
     assert (ei.value.code, ei.value.index) == (4, 2)
     with pytest.raises(R.IncorrectSubgroup):
         R.check_subgroup(g, good[:2] + [P])
+
+
+def test_c1_host_pieces_key_generation_and_proofs_of_knowledge():
+    """oracle/pyref_host.py (RECALLED, UNVERIFIABLE OFFLINE: rand_chacha / ark-ff sampling order): the host-side pieces
+    config C1 needs around the hot path — derive_rng_from_seed (seed.rs:7-14), Phase1::key_generation
+    (key_generation.rs:8-53), compute_g2_s / hash_to_g2 (helpers.rs:277-291,428-443), PublicKey::write
+    (public_key.rs:40-55) — are self-consistent: every generated point is a non-zero subgroup point, the three proofs of
+    knowledge verify under the oracle's pairing (verification.rs:83-133) and a tampered key is rejected; the digest of the
+    serialized key is pinned so that a drift of the restatement is visible."""
+    import hashlib
+    import pyref_host as H
+    cv = R.BLS12_377
+    assert H.chacha20_block(bytes(32), 0)[:2] == [0xade0b876, 0x903df1a0]  # ChaCha20 zero-key block (RFC 8439 family)
+    assert H.BLS12_377_G1_COFACTOR == 0x170b5d44300000000000000000000000
+    digest = hashlib.blake2b(b"challenge").digest()
+    pk, (tau, alpha, beta) = H.key_generation(cv, H.derive_rng_from_seed(b"seed-0"), digest)
+    assert 0 < tau < cv.r and 0 < alpha < cv.r and 0 < beta < cv.r and len({tau, alpha, beta}) == 3
+    for name, x in (("tau", tau), ("alpha", alpha), ("beta", beta)):
+        s, sx = pk[name + "_g1"]
+        assert s is not None and cv.g1.on_curve(s) and cv.g1.mul(s, cv.r) is None and cv.g1.mul(s, x) == sx
+        q = pk[name + "_g2"]
+        assert q is not None and cv.g2.on_curve(q) and cv.g2.mul(q, cv.r) is None
+    blob = H.public_key_bytes(cv, pk)
+    assert len(blob) == R.Phase1Parameters(cv, 10, 256).public_key_size == 576
+    assert hashlib.blake2b(blob).hexdigest()[:32] == "4bbb29864c7a94540671da4ed8bb1dd8"
+    assert H.verify_proofs_of_knowledge(cv, pk, digest)
+    bad = dict(pk)
+    bad["alpha_g2"] = cv.g2.mul(pk["alpha_g2"], 2)
+    assert not H.verify_proofs_of_knowledge(cv, bad, digest)
+    # the same seed gives the same key; a different transcript digest gives different G2 points
+    pk2, k2 = H.key_generation(cv, H.derive_rng_from_seed(b"seed-0"), digest)
+    assert H.public_key_bytes(cv, pk2) == blob and k2 == (tau, alpha, beta)
