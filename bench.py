@@ -180,6 +180,69 @@ def cpu_baseline(budget_s=20.0):
             "contribute_powers_per_s": (1 << k) / tc, "verify_powers_per_s": (1 << k) / tv}
 
 
+def run_extras(S, R, O, bw6_power, phase2_log2):
+    """One-step measurements of the other BASELINE configs through the host-buffer C ABI, reported beside the headline
+    (`extras`), never part of `value`:  C3 = BW6-761 phase-1 verify (subgroup checks + power_pairs MSM + the four device
+    pairing verdicts) of a 2^bw6_power-power response, C5 = phase 2's delta^-1 batch_mul of a 2^phase2_log2-element
+    query + its merge_pairs ratio MSM.  Each leg: one warm-up pass, one timed pass, a parity spot check."""
+    out = {}
+    cv, cid = R.BW6_761, S.BW6_761
+    k = bw6_power
+    N = 1 << k
+    rp, sp = R.Phase1Parameters(cv, k, 256), S.Phase1Parameters(cid, k, 256)
+    sc = lambda lab: int.from_bytes(hashlib.blake2b(lab, digest_size=64).digest(), "little") % (cv.r - 2) + 2  # noqa: E731
+    k0, k1 = [sc(b"bw6-0-%d" % i) for i in range(3)], [sc(b"bw6-1-%d" % i) for i in range(3)]
+    blank = S.phase1_initialization(sp, False)
+    chal = bytearray(sp.get_length(False))
+    S.phase1_computation(sp, blank, chal, False, False, S.CHECK_NO, *k0)
+    del blank
+    resp = bytearray(sp.get_length(True))
+    S.phase1_computation(sp, chal, resp, False, True, S.CHECK_NO, *k1)  # warm-up of the contribute leg
+    t = time.perf_counter()
+    S.phase1_computation(sp, chal, resp, False, True, S.CHECK_NO, *k1)
+    t_c = time.perf_counter() - t
+    o, _, sz = rp.split_offsets(False)[0]
+    oo, _, szo = rp.split_offsets(True)[0]
+    i0 = 1234 % (2 * N - 5)
+    ok = bytes(resp[oo + i0 * szo:oo + (i0 + 4) * szo]) == O.apply_powers(1, 0, bytes(chal[o + i0 * sz:o + (i0 + 4) * sz]), False, 3,
+                                                                         True, 4, tau=k1[0], first_power=i0)
+    del chal
+    newc = bytearray(sp.get_length(False))
+    seed = bytes(range(32))
+    S.phase1_verification_ratios(sp, resp, True, newc, False, seed=seed)
+    t = time.perf_counter()
+    S.phase1_verification_ratios(sp, resp, True, newc, False, seed=seed)  # raises on a bad verdict
+    t_v = time.perf_counter() - t
+    ok = ok and bytes(newc[o + i0 * sz:o + (i0 + 4) * sz]) == O.transcode(1, 0, bytes(resp[oo + i0 * szo:oo + (i0 + 4) * szo]), True, 3, False, 4)
+    out["C3_bw6_761_phase1"] = {"power": k, "verify_powers_per_s": N / t_v, "verify_ms": t_v * 1e3, "contribute_powers_per_s": N / t_c,
+                                "contribute_ms": t_c * 1e3, "verdict": True, "parity_spot_check": bool(ok),
+                                "what": "host buffers; verify = ss_phase1_verification_ratios (vectors + 4 device pairing checks)"}
+    del newc, resp
+    # C5
+    cv, cid, g = R.BLS12_377, S.BLS12_377, R.BLS12_377.g1
+    n = 1 << phase2_log2
+    sc = lambda lab: int.from_bytes(hashlib.blake2b(lab, digest_size=64).digest(), "little") % (cv.r - 2) + 2  # noqa: E731
+    h_before = S.apply_powers(cid, S.G1, g.encode(g.gen, False) * n, False, S.CHECK_NO, False, n, tau=sc(b"p2-tau"), first_power=1)
+    dinv = sc(b"p2-delta-inv")
+    buf = bytearray(h_before)
+    S.batch_mul(cid, S.G1, buf, dinv)
+    buf[:] = h_before
+    t = time.perf_counter()
+    S.batch_mul(cid, S.G1, buf, dinv)
+    t_mul = time.perf_counter() - t
+    ok = bytes(buf[:96 * 8]) == O.apply_powers(0, 0, h_before[:96 * 8], False, 3, False, 8, powers=[dinv] * 8)
+    after = bytes(buf)
+    S.merge_pairs(cid, S.G1, h_before, after, False, seed=bytes(range(32)))
+    t = time.perf_counter()
+    s_, sx_ = S.merge_pairs(cid, S.G1, h_before, after, False, seed=bytes(range(32)))
+    t_mp = time.perf_counter() - t
+    rok = O.apply_powers(0, 0, s_, False, 3, False, 1, powers=[dinv]) == sx_
+    out["C5_phase2_query"] = {"n": n, "batch_mul_elements_per_s": n / t_mul, "batch_mul_ms": t_mul * 1e3,
+                              "merge_pairs_pairs_per_s": n / t_mp, "merge_pairs_ms": t_mp * 1e3, "parity_spot_check": bool(ok),
+                              "ratio_check": bool(rok), "what": "host buffers; ss_batch_mul / ss_merge_pairs on uncompressed G1"}
+    return out
+
+
 _STDOUT_FD = None
 
 
@@ -203,6 +266,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pageable", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the one-step C3 (BW6-761) / C5 (phase 2) measurements")
+    ap.add_argument("--extras-bw6-power", type=int, default=21)
+    ap.add_argument("--extras-phase2-log2", type=int, default=20)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -487,6 +553,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del challenge, response, newc
+        torch.cuda.empty_cache()
+        try:
+            extras = run_extras(S, R, O, args.extras_bw6_power, args.extras_phase2_log2)
+        except Exception as exc:  # the headline line must not depend on the side measurements
+            extras = {"error": repr(exc)[:300]}
+
     if rank == 0:
         restore_stdout()
         print(json.dumps({
@@ -504,7 +579,7 @@ def main():
                      "verify": {"powers_per_s": N * args.steps / (v_ms * 1e-3), "ms_per_step": v_ms / args.steps,
                                 "includes": "partial-sum all-gather, reduction and the four device pairing checks on rank 0"}},
             "clocks": clocks, "gpu_launches": int(launches), "verdict_all_steps": verdict_ok,
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity_spot_check": parity,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity_spot_check": parity, "extras": extras,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
