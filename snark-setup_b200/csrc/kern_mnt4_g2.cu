@@ -1,15 +1,12 @@
 // Kernel instantiations for Mnt4G2 (MNT4/6-753 are exposed by the reference, setup-utils/src/converters.rs:18-45): the
 // generic kernels over a 24-limb field with a != 0 formulas and byte-granular serialisation.  Functional coverage, not
-// a tuned path: no endomorphism, no group FFT / QAP / pairing instantiations.
-#include "msm.cuh"
+// a tuned path: no endomorphism, no group FFT / QAP / pairing instantiations.  The bucket-MSM kernels of this group
+// live in kern_mnt4_g2_msm.cu (two translation units compile in parallel).
+#include "kernels.cuh"
 
 namespace ss {
 const GroupOps& ops_mnt4_g2() {
     static const GroupOps o = GroupLaunch<Mnt4G2>::ops();
-    return o;
-}
-const MsmOps& msm_ops_mnt4_g2() {
-    static const MsmOps o = MsmLaunch<Mnt4G2>::ops();
     return o;
 }
 }  // namespace ss
