@@ -315,7 +315,17 @@ int ss_groth16_params_new(const ss_phase1_params* p, const uint8_t* accumulator,
         for (size_t d = 0; d < D && concurrent; d++) {
             size_t free_b = 0, total_b = 0;
             if (cudaSetDevice(g_devices[d]) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) concurrent = false;
-            else if (per_dev[d] > total_b / 10 * 8) concurrent = false;
+            else {
+                // what the transforms can really get: free HBM plus the idle cached slabs of this device (lane_acquire
+                // re-grows them), not the card's total — other lanes / processes may hold memory
+                size_t idle = 0;
+                {
+                    std::lock_guard<std::mutex> lk(g_mu);
+                    for (Lane* l : g_lanes)
+                        if (!l->busy && l->device == g_devices[d]) idle += l->cap;
+                }
+                if (per_dev[d] > (free_b + idle) / 10 * 9 || per_dev[d] > total_b / 10 * 8) concurrent = false;
+            }
         }
     }
     if (concurrent) {

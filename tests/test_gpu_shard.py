@@ -238,3 +238,20 @@ def test_subgroup_verdict_on_off_curve_uncompressed_input(gname):
         with pytest.raises(S.IncorrectSubgroup) as ei:
             S.check_subgroup(cid, gid, bytes(buf), False)
         assert ei.value.index == 4
+
+
+def test_beta_g2_is_validated_without_a_new_challenge():
+    """verification.rs:199-201 reads beta_g2 with check_output_for_correctness whatever happens to the new challenge:
+    an infinite or off-subgroup beta_g2 is rejected by the aggregate-style call (new_challenge = None) too."""
+    cv, rp, sp, k0, k1, args, chal = _ceremony(3, 8, 31337)
+    resp = bytearray(O.phase1_computation(0, chal, rp.get_length(True), False, True, 3, *args, *k1))
+    S.phase1_verification_vectors(sp, bytes(resp), True, None, False, seed=bytes(32))
+    o, c, sz = rp.split_offsets(True)[4]
+    bad = bytearray(resp)
+    bad[o:o + sz] = cv.g2.encode(None, True)
+    with pytest.raises(S.PointAtInfinity):
+        S.phase1_verification_vectors(sp, bytes(bad), True, None, False, seed=bytes(32))
+    rng = random.Random(3)
+    bad[o:o + sz] = cv.g2.encode(_off_subgroup_point(cv.g2, rng), True)
+    with pytest.raises(S.InvalidData):  # Validate::Yes fails (arkworks reports InvalidData for a point outside the subgroup)
+        S.phase1_verification_vectors(sp, bytes(bad), True, None, False, seed=bytes(32))
