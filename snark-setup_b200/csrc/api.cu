@@ -186,6 +186,7 @@ struct Lane {
     uint8_t* buf = nullptr;  // one slab, carved per use
     size_t cap = 0;
     bool busy = false;
+    int prio = 0;  // 1: stream created with the device's highest priority (see lane_acquire)
 };
 std::vector<Lane*> g_lanes;
 
@@ -224,7 +225,11 @@ size_t tile_elems() {
     return t;
 }
 
-int lane_acquire(int device, size_t bytes, Lane** out) {
+// prio = 1 asks for a lane whose stream has the device's highest scheduling priority: pending blocks of its kernels are
+// dispatched before those of the normal lanes.  The verification loop gives it to the G2 vector, whose bucket reduction
+// ends in a ~10 ms latency-bound tail (a handful of warps): finishing that vector FIRST hides the tail behind the
+// throughput-bound kernels of the G1 vectors instead of leaving it exposed at the end of the call.
+int lane_acquire(int device, size_t bytes, Lane** out, int prio = 0) {
     Lane* ln = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -233,7 +238,7 @@ int lane_acquire(int device, size_t bytes, Lane** out) {
         Lane* fit = nullptr;
         Lane* big = nullptr;
         for (Lane* l : g_lanes) {
-            if (l->busy || l->device != device) continue;
+            if (l->busy || l->device != device || l->prio != prio) continue;
             if (l->cap >= bytes && (!fit || l->cap < fit->cap)) fit = l;
             if (!big || l->cap > big->cap) big = l;
         }
@@ -244,6 +249,7 @@ int lane_acquire(int device, size_t bytes, Lane** out) {
         if (!ln) {
             ln = new Lane();
             ln->device = device;
+            ln->prio = prio;
             g_lanes.push_back(ln);
         }
         ln->busy = true;
@@ -251,7 +257,11 @@ int lane_acquire(int device, size_t bytes, Lane** out) {
     // the caller's LaneGuard owns the lane from here on, so every error path below releases it
     *out = ln;
     CU(cudaSetDevice(device));
-    if (!ln->stream) CU(cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
+    if (!ln->stream) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&ln->stream, cudaStreamNonBlocking, ln->prio ? greatest : least));
+    }
     if (ln->cap < bytes) {
         if (ln->buf) CU(cudaFree(ln->buf));
         ln->buf = nullptr;

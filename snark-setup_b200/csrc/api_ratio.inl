@@ -41,7 +41,16 @@ struct RatioJob {
     const char* what;
     uint64_t rho_base = 0;   // global index of element 0 (ChaCha20 counter base) when the vector is a shard
     uint64_t own = 0;        // elements to subgroup-check / re-emit (0 = all n); n - own = 1 overlap element of a shard
+    int prio = 0;            // 1: run on a high-priority lane (lane_acquire)
 };
+
+bool priority_lanes() {  // $SS_PRIORITY_LANES=0 switches the high-priority G2 lane off (A/B)
+    static const bool on = [] {
+        const char* e = getenv("SS_PRIORITY_LANES");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
 
 int pick_window_bits(uint64_t pairs_per_tile) {
     int lg = 0;
@@ -110,7 +119,7 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     need += sort_b + bucket_b;
     LaneGuard lg;
     std::vector<std::vector<uint8_t>> keep;  // re-packed scalar staging, alive until the stream is synchronised
-    int rc = lane_acquire(device, need, &lg.l);
+    int rc = lane_acquire(device, need, &lg.l, j.prio);
     if (rc) return rc;
     cudaStream_t s = (!host && user_stream) ? user_stream : lg.l->stream;
     Carver cv(lg.l->buf);
@@ -456,6 +465,7 @@ static int phase1_verification_impl(const ss_phase1_params* p, const uint8_t* ou
                           out ? out + s0 * sz(*gs[v], compressed_new_challenge) : nullptr, compressed_new_challenge,
                           ps, ps + gs[v]->usize, names[v], s0};
             j.own = e0 - s0;
+            j.prio = (grp[v] == SS_G2 && want_ratio && priority_lanes()) ? 1 : 0;
             if ((r = run_ratio_vector(device, j, host, st))) {
                 g_err.index += s0;
                 return r;

@@ -1,15 +1,13 @@
 set -x
 cd $GRAFT_REPO_ROOT
-(time python -m pytest tests/test_gpu_parity.py -x -q) > gpurun_out/r02_gpu_tests_parity.log 2>&1
-tail -5 gpurun_out/r02_gpu_tests_parity.log
-(time python bench.py) > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err
-tail -3 gpurun_out/r02_bench_default.err
+for p in 18 20; do for pr in 0 1; do
+SS_PRIORITY_LANES=$pr python bench.py --power $p --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/r02_ab_prio${pr}_p$p.json 2> gpurun_out/r02_ab_prio${pr}_p$p.err
+done; done
 python - <<'P'
 import json
-d=json.loads(open('gpurun_out/r02_bench_default.json').read().strip().splitlines()[-1])
-print(round(d['value']), d['ms_per_step'], d['legs'], round(d['e2e']['value']), d['parity_spot_check'], d['verdict_all_steps'])
-print(json.dumps(d['extras'])[:1500])
-print(json.dumps(d['cpu_baseline'])[:600])
+for p in (18,20):
+  for pr in (0,1):
+    d=json.loads(open(f'gpurun_out/r02_ab_prio{pr}_p{p}.json').read().strip().splitlines()[-1])
+    print(p, pr, round(d['value']), round(d['legs']['contribute']['ms_per_step'],2), round(d['legs']['verify']['ms_per_step'],2), d['parity_spot_check'], d['verdict_all_steps'])
 P
-(time python bench.py --impl reference --steps 2 --warmup 1) > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err
-cut -c1-300 gpurun_out/r02_bench_reference.json
+python -m pytest tests/test_gpu_verify.py tests/test_gpu_shard.py -q 2>&1 | tail -2
