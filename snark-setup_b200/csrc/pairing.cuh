@@ -79,69 +79,85 @@ struct Bw6Pairing {
     SS_D static F mul_xi(const F& a) { return fp_neg(fp_dbl(fp_dbl(a))); }  // xi = -4
 };
 
-// c = a * b in F[w]/(w^6 - xi); every lane passes its own coefficient (lane k mod 6 <-> w^k)
+// Lane layout (one warp per check): lane = 6 s + k (mod 18) — every lane holds coefficient k = lane % 6 of the running
+// value, and the THREE lanes (k, s = 0..2) share the work of that coefficient: a product needs 6 F-multiplications per
+// coefficient, each lane does 2 and the partial sums are added over lanes k, k + 6, k + 12 (every lane adds the same
+// three values in the same order, so the copies stay identical); a sparse line multiplication is 1 F-multiplication per
+// lane.  (Round 1 had every lane do all 6: the check is pure latency — one warp on an SM — so the fewer multiplications
+// in sequence, the better: 18.7 -> see profiles/r02_pairing_latency.jsonl.)
+SS_D int lane_k() { return (int)(threadIdx.x % 6u); }
+SS_D int lane_s() { return (int)((threadIdx.x / 6u) % 3u); }
+
+template <class F>
+SS_D F ext_reduce3(const F& part, int k) {
+    return fp_add(fp_add(lane_get(part, k), lane_get(part, k + 6)), lane_get(part, k + 12));
+}
+
+// c = a * b in F[w]/(w^6 - xi); every lane passes its own coefficient (lane k <-> w^k)
 template <class C>
 SS_D typename C::F ext_mul(const typename C::F& a, const typename C::F& b, int k) {
     using F = typename C::F;
+    const int s = lane_s();
     F lo = F::zero(), hi = F::zero();  // hi collects the terms with i + j >= 6 (one multiplication by xi at the end)
 #pragma unroll 1
-    for (int i = 0; i < 6; i++) {
+    for (int ii = 0; ii < 2; ii++) {
+        const int i = 2 * s + ii;
         int j = k - i;
         const bool wrap = j < 0;
         if (wrap) j += 6;
         F t = fp_mul(lane_get(a, i), lane_get(b, j));
-        if (wrap) hi = fp_add(hi, t);
-        else lo = fp_add(lo, t);
+        // per-lane selection instead of a branch: the lanes of a warp take different (i, j)
+        F z = F::zero();
+        hi = fp_add(hi, wrap ? t : z);
+        lo = fp_add(lo, wrap ? z : t);
     }
-    return fp_add(lo, C::mul_xi(hi));
+    return ext_reduce3(fp_add(lo, C::mul_xi(hi)), k);
 }
 
-// f * (s0 + lx w^XPOS + ly w^3), s0 in Fq (times xi for the M-type twist), lx, ly in F
+// f * (s0 + lx w^XPOS + ly w^3), s0 in Fq (times xi for the M-type twist), lx, ly in F: one term per lane group s
 template <class C>
 SS_D typename C::F ext_mul_line(const typename C::F& f, const typename C::Fq& s0, const typename C::F& lx,
                                 const typename C::F& ly, int k) {
     using F = typename C::F;
-    F c = fscale(f, s0);
-    if (C::XI_ON_CONST) c = C::mul_xi(c);
-    {
-        int j = k - 3;
-        const bool wrap = j < 0;
-        if (wrap) j += 6;
-        F t = fp_mul(lane_get(f, j), ly);
-        c = fp_add(c, wrap ? C::mul_xi(t) : t);
-    }
-    {
-        int j = k - C::XPOS;
-        const bool wrap = j < 0;
-        if (wrap) j += 6;
-        F t = fp_mul(lane_get(f, j), lx);
-        c = fp_add(c, wrap ? C::mul_xi(t) : t);
-    }
-    return c;
+    const int s = lane_s();
+    // s = 0: f_k * s0 (* xi)   s = 1: f_{k-3} * ly   s = 2: f_{k-XPOS} * lx
+    const int off = s == 1 ? 3 : (s == 2 ? C::XPOS : 0);
+    int j = k - off;
+    const bool wrap = j < 0;
+    if (wrap) j += 6;
+    const F fj = lane_get(f, j);
+    F t0 = fscale(fj, s0);
+    if (C::XI_ON_CONST) t0 = C::mul_xi(t0);
+    F m = s == 1 ? ly : lx;
+    F t12 = fp_mul(fj, m);
+    F t12x = C::mul_xi(t12);
+    F part;
+    if (s == 0) part = t0;
+    else part = wrap ? t12x : t12;
+    return ext_reduce3(part, k);
 }
 
-// f * (c0 + c1 w + c3 w^3), all three in F — the lines of the ate Miller loop on a D-type twist
+// f * (c0 + c1 w + c3 w^3), all three in F — the lines of the ate Miller loop on a D-type twist; one term per lane group
 template <class C>
 SS_D typename C::F ext_mul_013(const typename C::F& f, const typename C::F& c0, const typename C::F& c1,
                                const typename C::F& c3, int k) {
     using F = typename C::F;
-    F c = fp_mul(f, c0);
-    {
-        int j = k - 1;
-        const bool wrap = j < 0;
-        if (wrap) j += 6;
-        F t = fp_mul(lane_get(f, j), c1);
-        c = fp_add(c, wrap ? C::mul_xi(t) : t);
-    }
-    {
-        int j = k - 3;
-        const bool wrap = j < 0;
-        if (wrap) j += 6;
-        F t = fp_mul(lane_get(f, j), c3);
-        c = fp_add(c, wrap ? C::mul_xi(t) : t);
-    }
-    return c;
+    const int s = lane_s();
+    const int off = s == 1 ? 1 : (s == 2 ? 3 : 0);
+    int j = k - off;
+    const bool wrap = j < 0;
+    if (wrap) j += 6;
+    const F c = s == 0 ? c0 : (s == 1 ? c1 : c3);
+    F t = fp_mul(lane_get(f, j), c);
+    F tx = C::mul_xi(t);
+    return ext_reduce3(wrap ? tx : t, k);
 }
+
+// The two pairings of a check are advanced by different lane groups: lanes with s == 1 carry the Miller point of
+// pairing 1, all others that of pairing 0; each lane computes the line of ITS pairing only and the coefficients are
+// broadcast from lane 0 (pairing 0) and lane 6 (pairing 1) for the two sparse multiplications every lane takes part in.
+SS_D int lane_pairing() { return lane_s() == 1 ? 1 : 0; }
+SS_D int lane_of_pairing(int j) { return 6 * j; }
 
 // Tate: f_{r,P0}(psi Q0) * f_{r,P1}(psi Q1), Miller points on G1 (see the header of this file for the lines)
 template <class C>
@@ -149,35 +165,40 @@ SS_D typename C::F miller_tate(const Affine<typename C::Fq>* P, const Affine<typ
     using F = typename C::F;
     using Fq = typename C::Fq;
     using G1 = typename C::G1;
-    Jac<Fq> T[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) T[j] = Jac<Fq>{P[j].x, P[j].y, Fq::one()};
+    const int my = lane_pairing();
+    const Affine<Fq> Pm = P[my];
+    const Affine<F> Qm = Q[my];
+    Jac<Fq> T = Jac<Fq>{Pm.x, Pm.y, Fq::one()};
     F f = k == 0 ? F::one() : F::zero();
 #pragma unroll 1
     for (int i = G1::GP::ORDER_BITS - 2; i >= 0; i--) {
         f = ext_mul<C>(f, f, k);
-#pragma unroll 1
-        for (int j = 0; j < 2; j++) {
-            const Jac<Fq>& t = T[j];
-            Fq X2 = fp_sqr(t.X), Y2 = fp_sqr(t.Y), Z2 = fp_sqr(t.Z);
+        {
+            Fq X2 = fp_sqr(T.X), Y2 = fp_sqr(T.Y), Z2 = fp_sqr(T.Z);
             Fq X2_3 = fp_add(fp_dbl(X2), X2);
-            Fq s0 = fp_sub(fp_mul(X2_3, t.X), fp_dbl(Y2));
+            Fq s0 = fp_sub(fp_mul(X2_3, T.X), fp_dbl(Y2));
             Fq sx = fp_neg(fp_mul(X2_3, Z2));
-            Fq sy = fp_dbl(fp_mul(fp_mul(t.Y, t.Z), Z2));
-            f = ext_mul_line<C>(f, s0, fscale(Q[j].x, sx), fscale(Q[j].y, sy), k);
-            T[j] = jac_dbl(t);
+            Fq sy = fp_dbl(fp_mul(fp_mul(T.Y, T.Z), Z2));
+            F lx = fscale(Qm.x, sx), ly = fscale(Qm.y, sy);
+            T = jac_dbl(T);
+#pragma unroll 1
+            for (int j = 0; j < 2; j++) {
+                const int src = lane_of_pairing(j);
+                f = ext_mul_line<C>(f, lane_get(s0, src), lane_get(lx, src), lane_get(ly, src), k);
+            }
         }
         const bool bit = (G1::GP::order(i >> 5) >> (i & 31)) & 1;
         if (bit && i != 0) {  // the last addition (T = -P) is a vertical line
+            Fq Z2 = fp_sqr(T.Z);
+            Fq N = fp_sub(T.Y, fp_mul(Pm.y, fp_mul(Z2, T.Z)));
+            Fq D = fp_mul(T.Z, fp_sub(T.X, fp_mul(Pm.x, Z2)));
+            Fq s0 = fp_sub(fp_mul(N, Pm.x), fp_mul(D, Pm.y));
+            F lx = fscale(Qm.x, fp_neg(N)), ly = fscale(Qm.y, D);
+            T = jac_madd(T, Pm);
 #pragma unroll 1
             for (int j = 0; j < 2; j++) {
-                const Jac<Fq>& t = T[j];
-                Fq Z2 = fp_sqr(t.Z);
-                Fq N = fp_sub(t.Y, fp_mul(P[j].y, fp_mul(Z2, t.Z)));
-                Fq D = fp_mul(t.Z, fp_sub(t.X, fp_mul(P[j].x, Z2)));
-                Fq s0 = fp_sub(fp_mul(N, P[j].x), fp_mul(D, P[j].y));
-                f = ext_mul_line<C>(f, s0, fscale(Q[j].x, fp_neg(N)), fscale(Q[j].y, D), k);
-                T[j] = jac_madd(t, P[j]);
+                const int src = lane_of_pairing(j);
+                f = ext_mul_line<C>(f, lane_get(s0, src), lane_get(lx, src), lane_get(ly, src), k);
             }
         }
     }
@@ -191,35 +212,40 @@ SS_D typename C::F miller_tate(const Affine<typename C::Fq>* P, const Affine<typ
 template <class C>
 SS_D typename C::F miller_ate(const Affine<typename C::Fq>* P, const Affine<typename C::F>* Q, int k) {
     using F = typename C::F;
+    using Fq = typename C::Fq;
     using PP = typename C::PP;
-    Jac<F> T[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) T[j] = Jac<F>{Q[j].x, Q[j].y, F::one()};
+    const int my = lane_pairing();
+    const Affine<Fq> Pm = P[my];
+    const Affine<F> Qm = Q[my];
+    Jac<F> T = Jac<F>{Qm.x, Qm.y, F::one()};
     F f = k == 0 ? F::one() : F::zero();
 #pragma unroll 1
     for (int i = PP::ATE_BITS - 2; i >= 0; i--) {
         f = ext_mul<C>(f, f, k);
-#pragma unroll 1
-        for (int j = 0; j < 2; j++) {
-            const Jac<F>& t = T[j];
-            F X2 = fp_sqr(t.X), Y2 = fp_sqr(t.Y), Z2 = fp_sqr(t.Z);
+        {
+            F X2 = fp_sqr(T.X), Y2 = fp_sqr(T.Y), Z2 = fp_sqr(T.Z);
             F X2_3 = fp_add(fp_dbl(X2), X2);
-            F c3 = fp_sub(fp_mul(X2_3, t.X), fp_dbl(Y2));
-            F c1 = fscale(fp_neg(fp_mul(X2_3, Z2)), P[j].x);
-            F c0 = fscale(fp_dbl(fp_mul(fp_mul(t.Y, t.Z), Z2)), P[j].y);
-            f = ext_mul_013<C>(f, c0, c1, c3, k);
-            T[j] = jac_dbl(t);
-        }
-        if ((PP::ate(i >> 5) >> (i & 31)) & 1) {
+            F c3 = fp_sub(fp_mul(X2_3, T.X), fp_dbl(Y2));
+            F c1 = fscale(fp_neg(fp_mul(X2_3, Z2)), Pm.x);
+            F c0 = fscale(fp_dbl(fp_mul(fp_mul(T.Y, T.Z), Z2)), Pm.y);
+            T = jac_dbl(T);
 #pragma unroll 1
             for (int j = 0; j < 2; j++) {
-                const Jac<F>& t = T[j];
-                F Z2 = fp_sqr(t.Z);
-                F N = fp_sub(t.Y, fp_mul(Q[j].y, fp_mul(Z2, t.Z)));
-                F D = fp_mul(t.Z, fp_sub(t.X, fp_mul(Q[j].x, Z2)));
-                F c3 = fp_sub(fp_mul(N, Q[j].x), fp_mul(D, Q[j].y));
-                f = ext_mul_013<C>(f, fscale(D, P[j].y), fscale(fp_neg(N), P[j].x), c3, k);
-                T[j] = jac_madd(t, Q[j]);
+                const int src = lane_of_pairing(j);
+                f = ext_mul_013<C>(f, lane_get(c0, src), lane_get(c1, src), lane_get(c3, src), k);
+            }
+        }
+        if ((PP::ate(i >> 5) >> (i & 31)) & 1) {
+            F Z2 = fp_sqr(T.Z);
+            F N = fp_sub(T.Y, fp_mul(Qm.y, fp_mul(Z2, T.Z)));
+            F D = fp_mul(T.Z, fp_sub(T.X, fp_mul(Qm.x, Z2)));
+            F c3 = fp_sub(fp_mul(N, Qm.x), fp_mul(D, Qm.y));
+            F c0 = fscale(D, Pm.y), c1 = fscale(fp_neg(N), Pm.x);
+            T = jac_madd(T, Qm);
+#pragma unroll 1
+            for (int j = 0; j < 2; j++) {
+                const int src = lane_of_pairing(j);
+                f = ext_mul_013<C>(f, lane_get(c0, src), lane_get(c1, src), lane_get(c3, src), k);
             }
         }
     }
