@@ -53,11 +53,17 @@ bool priority_lanes() {  // $SS_PRIORITY_LANES=0 switches the high-priority G2 l
 }
 
 int pick_window_bits(uint64_t pairs_per_tile) {
+    // c = log2(pairs) - offset: 2^offset points per bucket on average.  Measured (profiles/r02_ab_variants.md): offset 4
+    // with c <= 16 beats round 1's offset 5 / c <= 15 (2^20 pairs: c = 16, W = 8 windows instead of 9 and twice the
+    // bucket threads; accumulate 64.7 -> 54.0 ms per 2^20-power response, the reductions grow by 2 ms).
+    // $SS_MSM_C_OFFSET / $SS_MSM_C_MAX override for A/B runs.
+    static const int offset = [] { const char* e = getenv("SS_MSM_C_OFFSET"); return e ? atoi(e) : 4; }();
+    static const int cmax = [] { const char* e = getenv("SS_MSM_C_MAX"); int v = e ? atoi(e) : 16; return v < 2 ? 2 : (v > 16 ? 16 : v); }();
     int lg = 0;
     while ((1ull << (lg + 1)) <= pairs_per_tile) lg++;
-    int c = lg - 5;
+    int c = lg - offset;
     if (c < 2) c = 2;
-    if (c > 15) c = 15;
+    if (c > cmax) c = cmax;
     return c;
 }
 
