@@ -207,7 +207,9 @@ bool concurrent_vectors() {
 // Elements per device tile.  k_scalar_mul does the same work in every thread, so its blocks finish in waves:
 // the default is 8 whole waves of the G1 kernel (148 SMs x 4 resident blocks x 128 threads = 75 776
 // elements per wave; the G2 kernel's waves are half that).  Measured (profiles/r01_ab_variants.md): wave quantisation is
-// NOT visible (2^18: 251 ms, 4 waves: 248 ms), larger tiles win 1.3 % through fewer normalisation tails.  $SS_TILE_ELEMS / $SS_TILE_LOG2 override.
+// NOT visible (2^18: 251 ms, 4 waves: 248 ms), larger tiles win through fewer normalisation tails: 8 waves +1.3 % over 2^18
+// (round 1), 16 waves another +0.85 % on the 2^22 contribute (1657.7 -> 1643.7 ms, profiles/r02_ab_variants.md).
+// $SS_TILE_ELEMS / $SS_TILE_LOG2 override.
 size_t tile_elems() {
     static size_t t = [] {
         if (const char* e = getenv("SS_TILE_ELEMS")) {
@@ -220,7 +222,7 @@ size_t tile_elems() {
             if (l > 24) l = 24;
             return (size_t)1 << l;
         }
-        return (size_t)8 * 75776;
+        return (size_t)16 * 75776;
     }();
     return t;
 }

@@ -70,7 +70,7 @@ int pick_window_bits(uint64_t pairs_per_tile) {
 size_t ratio_tile_elems() {
     static size_t t = [] {
         const char* e = getenv("SS_RATIO_TILE_LOG2");
-        int l = e ? atoi(e) : 20;
+        int l = e ? atoi(e) : 21;  // 2^21: -7 ms per 2^22 verify round against 2^20 (profiles/r02_ab_variants.md)
         if (l < 8) l = 8;
         if (l > 24) l = 24;
         return (size_t)1 << l;
