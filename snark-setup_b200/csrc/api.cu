@@ -6,7 +6,7 @@
 //   apply_powers                          phase1/src/helpers/buffers.rs:77-97
 //   Phase1::computation (Groth16)         phase1/src/computation.rs:40-193
 // The reference walks each vector in `batch_size` windows on rayon threads; results do not depend
-// on the windowing, so here each vector is cut into device tiles (default 606 208 elements) that are
+// on the windowing, so here each vector is cut into device tiles (default 1 212 416 elements) that are
 // pipelined over two CUDA streams (H2D of tile k+1 overlaps the kernels of tile k), the five vectors
 // of a call run on concurrent lanes, and with several devices every vector is split D ways.
 #ifndef __CUDACC__
