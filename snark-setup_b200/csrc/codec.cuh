@@ -183,7 +183,7 @@ SS_HD bool in_subgroup_rmul(const Affine<typename G::F>& p) {
 // (g1.rs / g2.rs).  u = 0x8508c00000000001 has 7 set bits: 63+6 group operations per [u] instead of
 // 253+87, identical for every lane.  tests/test_oracle_cpu.py checks verdict equality with the
 // r-multiplication on subgroup points, random curve points, pure cofactor torsion and mixed points.
-// BW6-761 G1 has its own endomorphism test below; BW6-761 G2 keeps the r-multiplication.
+// BW6-761 G1 and G2 have their own endomorphism tests below; the MNT groups keep the r-multiplication.
 // -DSS_SUBGROUP_RMUL forces the reference algorithm everywhere.
 constexpr unsigned long long kBls377U = 0x8508c00000000001ull;
 
@@ -237,31 +237,47 @@ SS_HD bool in_subgroup_endo(const Affine<Fp2<Bls377Fq>>& p, Bls377G2*) {
     Endo<Bls377G2>::apply(1, x, y);  // psi(P)
     return jac_eq_affine(up, x, y);
 }
-// ---- endomorphism subgroup test for BW6-761 G1 --------------------------------------------------------
-// phi(x, y) = (beta x, y) acts on G1 as lambda with lambda^2 + lambda + 1 = 0 (mod r), and
-//     (u + 1) + (u^3 - u^2 + 1) * lambda = 0 (mod r)        (u = the BLS12-377 seed, checked in tests),
-// so psi = (u + 1) + (u^3 - u^2 + 1) phi kills G1.  Its norm a^2 - ab + b^2 is 3r: psi = (1 - phi) psi' up to a
-// unit of Z[phi], with ker psi' = G1 (order r) and ker(1 - phi) = {O, (0, +-sqrt(-1))}.  q = 3 (mod 4), so those
-// two points are not rational on y^2 = x^3 - 1 and, phi being defined over Fq, psi(P) = O for P in E(Fq) forces
-// psi'(P) = O: the test accepts EXACTLY G1 — the same predicate as the reference's r-multiplication
-// (elements.rs:138-142) at 252 doublings + 28 additions instead of 376 + 134.  (gnark-crypto's bw6-761 G1 uses
-// the same short vector.)  G2 keeps the r-multiplication: on y^2 = x^3 + 4 the point (0, 2) has order 3, is fixed
-// by phi and IS killed by psi, so the analogous test would accept G2 + <(0, 2)>.
-SS_HD bool in_subgroup_endo(const Affine<Fp<Bw6Fq>>& p, Bw6G1*) {
+// ---- endomorphism subgroup tests for BW6-761 ------------------------------------------------------------------------
+// phi(x, y) = (beta x, y) acts on the order-r subgroup as lambda, lambda^2 + lambda + 1 = 0 (mod r).  For a lattice
+// vector (a, b), a + b lambda = 0 (mod r), of norm a^2 - ab + b^2 EXACTLY r (tools/gen_constants.py, Bw6G{1,2}SubgroupVec;
+// the reduced GLV basis consists of such vectors), psi = a + b phi is an endomorphism of degree r that kills the
+// subgroup, hence ker psi IS the subgroup: psi(P) = O accepts exactly the order-r points, the same predicate as the
+// reference's r-multiplication (elements.rs:138-142), at 189 doublings + ~95 additions (joint sparse form over P, phi(P),
+// P + phi(P), P - phi(P); the digits are constants, so control flow is uniform) instead of 376 + 134.
+// Round 1 used the sparse vector (u + 1, u^3 - u^2 + 1) for G1, whose norm is 3r: sound there only because the extra
+// 3-torsion kernel is irrational when q = 3 (mod 4), and unusable for G2 (on y^2 = x^3 + 4 the points (0, +-2) are
+// rational and in that kernel).  The norm-r vector needs no such argument and measures faster on both groups
+// (k_subgroup<bw6 g2> 39.4 -> 20.4 ms per 2^16 elements; profiles/r02_ab_variants.md).
+template <class Glv, class V>
+SS_HD bool in_subgroup_norm_r(const Affine<Fp<Bw6Fq>>& p) {
     using F = Fp<Bw6Fq>;
     if (p.inf) return true;
     F beta;
 #pragma unroll
-    for (int i = 0; i < 24; i++) beta.l[i] = Bw6G1Glv::beta(i);
-    Affine<F> phip{fp_mul(p.x, beta), p.y, false};
-    Jac<F> t = jac_mul_u<F>(phip);              // u phi(P)
-    t = jac_madd(t, affine_neg(phip));          // (u - 1) phi(P)
-    t = jac_mul_u<F>(t);                        // (u^2 - u) phi(P)
-    t = jac_mul_u<F>(t);                        // (u^3 - u^2) phi(P)
-    t = jac_madd(t, phip);                      // (u^3 - u^2 + 1) phi(P)
-    Jac<F> s = jac_madd(jac_mul_u<F>(p), p);    // (u + 1) P
-    return jac_add(t, s).is_identity();
+    for (int i = 0; i < 24; i++) beta.l[i] = Glv::beta(i);
+    const Affine<F> phip{fp_mul(p.x, beta), p.y, false};
+    const Jac<F> jp{p.x, p.y, F::one()};
+    const Jac<F> sum = jac_madd(jp, phip);               // P + phi(P)
+    const Jac<F> dif = jac_madd(jp, affine_neg(phip));   // P - phi(P)
+    Jac<F> acc = Jac<F>::identity();
+#pragma unroll 1
+    for (int i = 0; i < V::LEN; i++) {
+        acc = jac_dbl(acc);
+        const int d = (int)V::digit(i), da = d / 3 - 1, db = d % 3 - 1;
+        if (da != 0 && db == 0) {
+            acc = jac_madd(acc, da > 0 ? p : affine_neg(p));
+        } else if (da == 0 && db != 0) {
+            acc = jac_madd(acc, db > 0 ? phip : affine_neg(phip));
+        } else if (da != 0) {  // both: +-(P + phi P) when the signs agree, +-(P - phi P) otherwise
+            Jac<F> t = da == db ? sum : dif;
+            if (da < 0) t.Y = fp_neg(t.Y);
+            acc = jac_add(acc, t);
+        }
+    }
+    return acc.is_identity();
 }
+SS_HD bool in_subgroup_endo(const Affine<Fp<Bw6Fq>>& p, Bw6G1*) { return in_subgroup_norm_r<Bw6G1Glv, Bw6G1SubgroupVec>(p); }
+SS_HD bool in_subgroup_endo(const Affine<Fp<Bw6Fq>>& p, Bw6G2*) { return in_subgroup_norm_r<Bw6G2Glv, Bw6G2SubgroupVec>(p); }
 template <class G>
 SS_HD bool in_subgroup_endo(const Affine<typename G::F>& p, G*) {
     return in_subgroup_rmul<G>(p);

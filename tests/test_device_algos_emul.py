@@ -113,8 +113,9 @@ def test_subgroup_test_equals_r_multiplication(L, gid):
         pts += [(q - 1, 0), (0, 1), (0, q - 1)]
     if gid == 2:
         # BW6-761 G1 (y^2 = x^3 - 1): the three points of order 2, small-order torsion obtained by clearing most of
-        # the group order from random points, subgroup points shifted by such torsion, and the relation the test
-        # rests on: (u + 1) + (u^3 - u^2 + 1) lambda = 0 (mod r), norm 3r, q = 3 (mod 4)
+        # the group order from random points, subgroup points shifted by such torsion.  (The device test is psi = a + b phi
+        # with a^2 - ab + b^2 = r, codec.cuh; round 1's sparse vector (u + 1, u^3 - u^2 + 1) has norm 3r — asserted below
+        # for the record — and was sound on G1 only because q = 3 (mod 4) keeps the extra 3-torsion irrational.)
         p6 = g.F.p
         w = next(pow(c, (p6 - 1) // 3, p6) for c in range(2, 50) if pow(c, (p6 - 1) // 3, p6) != 1)
         pts += [(1, 0), (w, 0), (w * w % p6, 0)]
@@ -140,6 +141,35 @@ def test_subgroup_test_equals_r_multiplication(L, gid):
                 if Q is not None:
                     assert not g.in_subgroup(Q)
                     pts += [Q, g.add(Q, g.mul(g.gen, rng.randrange(1, g.r)))]
+    if gid == 3:
+        # BW6-761 G2 (y^2 = x^3 + 4): the test is psi = a + b phi with a^2 - ab + b^2 = r EXACTLY (degree r, kernel = G2).
+        # The points the sparse norm-3r vector of G1 would wrongly accept — the rational 3-torsion (0, +-2) and subgroup
+        # points shifted by it — must be rejected, like every other torsion of the cofactor.
+        p6 = g.F.p
+        T3 = (0, 2)
+        assert g.on_curve(T3) and g.mul(T3, 3) is None and not g.in_subgroup(T3)
+        pts += [T3, g.neg(T3)]
+        for _ in range(3):
+            Qs = g.mul(g.gen, rng.randrange(1, g.r))
+            pts += [g.add(Qs, T3), g.add(Qs, g.neg(T3))]
+        # small-order torsion from the cofactor: clear the group order but a small prime power
+        from math import isqrt
+        aa, bb = p6, g.F.sqrt((-3) % p6)
+        while bb > isqrt(p6):
+            aa, bb = bb, aa % bb
+        x0, y0 = bb, isqrt((p6 - bb * bb) // 3)
+        assert x0 * x0 + 3 * y0 * y0 == p6
+        Pr = rnd()
+        orders = [p6 + 1 - t for t in (2 * x0, -2 * x0, x0 + 3 * y0, -x0 - 3 * y0, x0 - 3 * y0, 3 * y0 - x0)]
+        n = next(o for o in orders if o % g.r == 0 and g.mul(Pr, o) is None)
+        h = n // g.r
+        small = [f for f in (2, 3, 4, 5, 7, 9, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47) if h % f == 0]
+        assert 3 in small
+        for f in small:
+            Q = g.mul(rnd(), n // f)
+            if Q is not None:
+                assert not g.in_subgroup(Q)
+                pts += [Q, g.add(Q, g.mul(g.gen, rng.randrange(1, g.r)))]
     for P in pts:
         rc = L.emul_in_subgroup(gid, g.encode(P, 0))
         assert rc == (3 if g.in_subgroup(P) else 0), (g.name, P, rc)
