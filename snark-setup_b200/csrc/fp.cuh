@@ -412,7 +412,7 @@ inline unsigned long long ss_op_count[3][32] = {};
 
 template <class P>
 SS_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
-#if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+#if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE) && !defined(SS_MULONLY_INLINE)
     return fp_mul_call<P>(a, b);
 #else
     SS_COUNT_OP(0, P::N);
@@ -499,7 +499,7 @@ template <class P>
 SS_HD Fp<P> fp_sqr(const Fp<P>& a) {
 #if defined(SS_NO_DEDICATED_SQR)
     return fp_mul(a, a);
-#elif defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+#elif defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE) && !defined(SS_SQR_INLINE)
     return fp_sqr_call<P>(a);
 #else
     SS_COUNT_OP(1, P::N);

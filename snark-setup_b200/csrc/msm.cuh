@@ -304,8 +304,10 @@ __global__ void __launch_bounds__(128, GL::SMUL_MINB) k_msm_accumulate_pair(MsmA
 // k * P for a small k (Jacobian base)
 template <class F>
 SS_D Jac<F> jac_mul_small(const Jac<F>& p, uint32_t k) {
-    Jac<F> acc = Jac<F>::identity();
-    for (int b = 31; b >= 0; b--) {
+    if (k == 0) return Jac<F>::identity();
+    // start below the leading bit: a serial tail kernel pays for every doubling, also those of the identity
+    Jac<F> acc = p;
+    for (int b = 30 - __clz(k); b >= 0; b--) {
         acc = jac_dbl(acc);
         if ((k >> b) & 1) acc = jac_add(acc, p);
     }
@@ -351,24 +353,28 @@ __global__ void __launch_bounds__(128) k_msm_reduce1(MsmReduceArgs a) {
     store_jac<G>(a.segres, total, t, r);
 }
 
-// grid (W, 2), 32 threads: tree over the segments of one window
+// grid (W, 2), REDUCE2_THREADS<F> threads: every thread sums a slice of the window's segment results, then a
+// shared-memory tree (log2 T dependent additions instead of the T - 1 a single finishing thread would chain)
+template <class F>
+struct Reduce2Threads {
+    static constexpr int value = sizeof(Jac<F>) * 128 <= 40960 ? 128 : (sizeof(Jac<F>) * 64 <= 40960 ? 64 : 32);
+};
 template <class G>
 __global__ void k_msm_reduce2(MsmReduceArgs a) {
     using F = typename G::F;
-    __shared__ Jac<F> part[32];
+    constexpr int T = Reduce2Threads<F>::value;
+    __shared__ Jac<F> part[T];
     const uint64_t sw = (uint64_t)blockIdx.y * a.W + blockIdx.x;
     const uint64_t total = (uint64_t)2 * a.W * a.nseg;
-    const uint32_t per = (a.nseg + 31) / 32;
     Jac<F> s = Jac<F>::identity();
-    for (uint32_t k = threadIdx.x * per; k < min(a.nseg, (threadIdx.x + 1) * per); k++)
-        s = jac_add(s, load_jac<G>(a.segres, total, sw * a.nseg + k));
+    for (uint32_t k = threadIdx.x; k < a.nseg; k += T) s = jac_add(s, load_jac<G>(a.segres, total, sw * a.nseg + k));
     part[threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        Jac<F> r = part[0];
-        for (int k = 1; k < 32; k++) r = jac_add(r, part[k]);
-        store_jac<G>(a.winres, (uint64_t)2 * a.W, sw, r);
+    for (int h = T / 2; h > 0; h >>= 1) {
+        if ((int)threadIdx.x < h) part[threadIdx.x] = jac_add(part[threadIdx.x], part[threadIdx.x + h]);
+        __syncthreads();
     }
+    if (threadIdx.x == 0) store_jac<G>(a.winres, (uint64_t)2 * a.W, sw, part[0]);
 }
 
 // 2 threads: Horner over windows, normalise, encode uncompressed
@@ -377,8 +383,8 @@ __global__ void k_msm_reduce3(MsmReduceArgs a) {
     using F = typename G::F;
     const int which = threadIdx.x;
     if (which > 1 || blockIdx.x != 0) return;
-    Jac<F> r = Jac<F>::identity();
-    for (int w = a.W - 1; w >= 0; w--) {
+    Jac<F> r = load_jac<G>(a.winres, (uint64_t)2 * a.W, (uint64_t)which * a.W + a.W - 1);
+    for (int w = a.W - 2; w >= 0; w--) {
         for (int k = 0; k < a.c; k++) r = jac_dbl(r);
         r = jac_add(r, load_jac<G>(a.winres, (uint64_t)2 * a.W, (uint64_t)which * a.W + w));
     }
@@ -419,7 +425,7 @@ struct MsmLaunch {
     static void reduce(const MsmReduceArgs& a, cudaStream_t s) {
         const uint64_t t1 = (uint64_t)2 * a.W * a.nseg;
         k_msm_reduce1<G><<<(unsigned)((t1 + 127) / 128), 128, 0, s>>>(a);
-        k_msm_reduce2<G><<<dim3(a.W, 2), 32, 0, s>>>(a);
+        k_msm_reduce2<G><<<dim3(a.W, 2), Reduce2Threads<typename G::F>::value, 0, s>>>(a);
         k_msm_reduce3<G><<<1, 32, 0, s>>>(a);
     }
     static MsmOps ops() { return MsmOps{&fill_identity, &accumulate, &reduce}; }
