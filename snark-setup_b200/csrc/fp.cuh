@@ -230,6 +230,48 @@ SS_HD Fp<P> fp_mul_inl(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// ---- K independent products, row-interleaved --------------------------------------------------------
+// r[k] = a[k] * b[k] / R for k < K, with the operand-scanning rows of the K products issued in turn.  One product's
+// rows are one long dependency chain (carry into carry, reduction factor from limb 0); a warp that is alone on its
+// scheduler (the Fq2 kernels: 255 registers, 2 warps per scheduler) issues 26 % of the cycles on it.  K chains side by
+// side give ptxas independent work to fill the multiplier pipe from ONE warp.  Used by the out-of-line Fq2 units of
+// fp2.cuh (K = 3: Karatsuba, K = 2: complex squaring).  Same operand bounds as fp_mul_inl.
+template <class P, int K>
+SS_HD void fp_mul_xk_inl(const Fp<P> (&a)[K], const Fp<P> (&b)[K], Fp<P> (&r)[K]) {
+    constexpr int N = P::N;
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t X[K][N], Y[K][N];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            X[k][j] = mul_lo(a[k].l[j], b[k].l[0]);
+            X[k][j + 1] = mul_hi(a[k].l[j], b[k].l[0]);
+            Y[k][j] = mul_lo(a[k].l[j + 1], b[k].l[0]);
+            Y[k][j + 1] = mul_hi(a[k].l[j + 1], b[k].l[0]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) mont_reduce_step<P>(X[k], Y[k]);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+#pragma unroll
+        for (int k = 0; k < K; k++) mont_step<P>(Y[k], X[k], a[k].l, b[k].l[i]);
+        if (i + 1 < N) {
+#pragma unroll
+            for (int k = 0; k < K; k++) mont_step<P>(X[k], Y[k], a[k].l, b[k].l[i + 1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        r[k].l[0] = add_cc(X[k][0], Y[k][1]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) r[k].l[j] = addc_cc(X[k][j], Y[k][j + 1]);
+        r[k].l[N - 1] = addc(X[k][N - 1], 0);
+        fp_final_sub<P>(r[k].l);
+    }
+}
+
 // ---- sum of two products ----------------------------------------------------------------------------
 // (a*b + c*d) / R mod p with ONE interleaved reduction: 2 N^2 products + N^2 reduction instead of the 4 N^2 of two
 // multiplications.  Used by the lane-split Fq2 arithmetic (fp2l.cuh), where one lane computes a0 b0 + a1 (-5 b1) and

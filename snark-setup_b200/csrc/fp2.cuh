@@ -76,9 +76,56 @@ SS_HD Fp2<P> fp_dbl(const Fp2<P>& a) {
     return Fp2<P>{fp_dbl(a.c0), fp_dbl(a.c1)};
 }
 
+// Out-of-line Fq2 units (device, NR = -5, <= 12 limbs): ONE call per Fq2 product / square instead of 3 / 2 calls of
+// the base multiplier, with the base products row-interleaved (fp_mul_xk_inl) so that a single warp has 3 / 2
+// independent carry chains in flight.  Measured SLOWER (k_scalar_mul<G2> 83.1 -> 90.6 ms per 2^19 launch,
+// profiles/r02_ab_variants.md): the unit needs ~170 registers, so its callers spill their Jacobian state around every
+// call.  Off by default; -DSS_FP2_UNITS=1 builds it; tests/emul checks the bodies either way.
+#ifndef SS_FP2_UNITS
+#define SS_FP2_UNITS 0
+#endif
+template <class P>
+SS_HD Fp2<P> fp2_mul_body(const Fp2<P>& a, const Fp2<P>& b) {
+    const Fp<P> x[3] = {a.c0, a.c1, fp_add_nr(a.c0, a.c1)};
+    const Fp<P> y[3] = {b.c0, b.c1, fp_add_nr(b.c0, b.c1)};
+    Fp<P> v[3];
+    fp_mul_xk_inl<P, 3>(x, y, v);
+    Fp2<P> r;
+    r.c1 = fp_sub(fp_sub(v[2], v[0]), v[1]);
+    r.c0 = fp_sub(v[0], fp_mul5(v[1]));
+    return r;
+}
+template <class P>
+SS_HD Fp2<P> fp2_sqr_body(const Fp2<P>& a) {
+    const Fp<P> x[2] = {a.c0, fp_add_nr(a.c0, a.c1)};
+    const Fp<P> y[2] = {a.c1, fp_sub(a.c0, fp_mul5(a.c1))};
+    Fp<P> v[2];
+    fp_mul_xk_inl<P, 2>(x, y, v);
+    const Fp<P> v2 = fp_dbl(v[0]);
+    Fp2<P> r;
+    r.c0 = fp_add(v[1], fp_dbl(v2));
+    r.c1 = v2;
+    return r;
+}
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Fp2<P> fp2_mul_call(Fp2<P> a, Fp2<P> b) {
+    return fp2_mul_body(a, b);
+}
+template <class P>
+__device__ __noinline__ Fp2<P> fp2_sqr_call(Fp2<P> a) {
+    return fp2_sqr_body(a);
+}
+#endif
+template <class P>
+constexpr bool kFp2Units = SS_FP2_UNITS && Fp2Config<P>::NR == -5 && P::N <= 12;
+
 // Karatsuba: 3 base multiplications
 template <class P>
 SS_HD Fp2<P> fp_mul(const Fp2<P>& a, const Fp2<P>& b) {
+#if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+    if constexpr (kFp2Units<P>) return fp2_mul_call<P>(a, b);
+#endif
     Fp<P> v0 = fp_mul(a.c0, b.c0);
     Fp<P> v1 = fp_mul(a.c1, b.c1);
 #if defined(SS_FP2_REDUCED_SUMS)
@@ -97,6 +144,9 @@ SS_HD Fp2<P> fp_mul(const Fp2<P>& a, const Fp2<P>& b) {
 // c0 = a0^2 - 5 a1^2 = (a0 + a1)(a0 - 5 a1) + 4 a0 a1 ;  c1 = 2 a0 a1
 template <class P>
 SS_HD Fp2<P> fp_sqr(const Fp2<P>& a) {
+#if defined(__CUDA_ARCH__) && !defined(SS_MUL_INLINE)
+    if constexpr (kFp2Units<P>) return fp2_sqr_call<P>(a);
+#endif
     if constexpr (Fp2Config<P>::NR != -5) {
         // c0 = a0^2 + NR a1^2 = (a0 + a1)(a0 + NR a1) - (NR + 1) a0 a1 ;  c1 = 2 a0 a1
         Fp<P> v = fp_mul(a.c0, a.c1);

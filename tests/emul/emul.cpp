@@ -304,6 +304,17 @@ int emul_fp_mul2(const uint8_t* a, const uint8_t* b, const uint8_t* c, const uin
     return 0;
 }
 
+// out-of-line Fq2 units (fp2.cuh: row-interleaved Karatsuba product / complex square); op 0 = product, 1 = square
+int emul_fp2_unit(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    typedef Bls377Fq P;
+    Fp2<P> x{fp_to_mont(load_raw<P>(a)), fp_to_mont(load_raw<P>(a + 48))};
+    Fp2<P> y{fp_to_mont(load_raw<P>(b)), fp_to_mont(load_raw<P>(b + 48))};
+    Fp2<P> r = op == 0 ? fp2_mul_body(x, y) : fp2_sqr_body(x);
+    store_raw<P>(out, fp_from_mont(r.c0));
+    store_raw<P>(out + 48, fp_from_mont(r.c1));
+    return 0;
+}
+
 // lane-split Fq2 product / square through the pure per-lane functions of fp2l.cuh: both lanes evaluated in turn
 int emul_fp2l_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     typedef Bls377Fq P;

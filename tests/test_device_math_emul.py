@@ -169,3 +169,8 @@ def test_lane_split_fq2_product_and_square(L):
         assert L.emul_fp2l_op(1, ab, bb, out) == 0
         q = F2.sqr(a)
         assert out.raw == tb(q[0], nb) + tb(q[1], nb), it
+        # the out-of-line per-thread units (row-interleaved base products) give the same values
+        assert L.emul_fp2_unit(0, ab, bb, out) == 0
+        assert out.raw == tb(m[0], nb) + tb(m[1], nb), it
+        assert L.emul_fp2_unit(1, ab, bb, out) == 0
+        assert out.raw == tb(q[0], nb) + tb(q[1], nb), it
