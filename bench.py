@@ -207,6 +207,7 @@ def run_extras(S, R, O, bw6_power, phase2_log2):
     ok = bytes(resp[oo + i0 * szo:oo + (i0 + 4) * szo]) == O.apply_powers(1, 0, bytes(chal[o + i0 * sz:o + (i0 + 4) * sz]), False, 3,
                                                                          True, 4, tau=k1[0], first_power=i0)
     del chal
+    progress("extras: C3 contribute done")
     newc = bytearray(sp.get_length(False))
     seed = bytes(range(32))
     S.phase1_verification_ratios(sp, resp, True, newc, False, seed=seed)
@@ -214,6 +215,7 @@ def run_extras(S, R, O, bw6_power, phase2_log2):
     S.phase1_verification_ratios(sp, resp, True, newc, False, seed=seed)  # raises on a bad verdict
     t_v = time.perf_counter() - t
     ok = ok and bytes(newc[o + i0 * sz:o + (i0 + 4) * sz]) == O.transcode(1, 0, bytes(resp[oo + i0 * szo:oo + (i0 + 4) * szo]), True, 3, False, 4)
+    progress("extras: C3 measured")
     out["C3_bw6_761_phase1"] = {"power": k, "verify_powers_per_s": N / t_v, "verify_ms": t_v * 1e3, "contribute_powers_per_s": N / t_c,
                                 "contribute_ms": t_c * 1e3, "verdict": True, "parity_spot_check": bool(ok),
                                 "what": "host buffers; verify = ss_phase1_verification_ratios (vectors + 4 device pairing checks)"}
@@ -244,6 +246,13 @@ def run_extras(S, R, O, bw6_power, phase2_log2):
 
 
 _STDOUT_FD = None
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """leg boundaries on stderr (stdout carries the one JSON line only)"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %7.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
 
 
 def restore_stdout():
@@ -269,7 +278,11 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the one-step C3 (BW6-761) / C5 (phase 2) measurements")
     ap.add_argument("--extras-bw6-power", type=int, default=21)
     ap.add_argument("--extras-phase2-log2", type=int, default=20)
+    ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baseline()), flush=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -450,6 +463,7 @@ def main():
         ok = ok and newc[ou: ou + szu].cpu().numpy().tobytes() == O.transcode(0, 1, got, True, 3, False, 1)
     parity = all_ok(ok)
 
+    progress("device-resident legs and parity spot check done")
     # ---- e2e: host buffers through the C ABI, every copy inside the timed region ---------------------------------
     e2e = None
     if not args.no_e2e:
@@ -494,12 +508,14 @@ def main():
                             "+ new challenge D2H; whole ceremony = N x",
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "host_memory": "pinned",
                "matches_device_path": same, "verdict": vd}
+        progress("e2e (pinned) done")
         if not args.no_pageable:
             p_steps = max(1, min(args.steps, 3))
             dt, same, vd = run_e2e(False, p_steps)
             e2e["pageable"] = {"value": N * p_steps / dt, "unit": "powers/s", "steps": p_steps,
                                "ms_per_step": dt / p_steps * 1e3, "matches_device_path": same, "verdict": vd}
 
+    progress("e2e legs done")
     # ---- roofline of the dominant kernels ------------------------------------------------------------------------
     peaks = {}
     try:
@@ -551,7 +567,16 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+        # in a child process: the CPU port is test infrastructure, and nothing it does (or a crash in it) may cost the
+        # headline line
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], capture_output=True, text=True,
+                               timeout=600)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            cpu = json.loads(lines[-1]) if r.returncode == 0 and lines else {"error": "exit %d: %s" % (r.returncode, r.stderr[-200:])}
+        except Exception as exc:
+            cpu = {"error": repr(exc)[:300]}
+        progress("cpu baseline done")
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -561,6 +586,7 @@ def main():
             extras = run_extras(S, R, O, args.extras_bw6_power, args.extras_phase2_log2)
         except Exception as exc:  # the headline line must not depend on the side measurements
             extras = {"error": repr(exc)[:300]}
+        progress("extras done")
 
     if rank == 0:
         restore_stdout()

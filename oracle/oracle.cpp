@@ -565,7 +565,11 @@ Jac<typename G::F> msm_pippenger(const Aff<typename G::F>* pts, const uint64_t* 
     std::vector<Jac<F>> window_sums(digits_count);
 #pragma omp parallel for schedule(dynamic, 1)
     for (size_t w = 0; w < digits_count; w++) {
-        std::vector<Jac<F>> buckets((size_t)1 << (c - 1), Jac<F>::identity());
+        // digits lie in [-2^(c-1), 2^(c-1)) — except the LAST one, which takes the final carry back and reaches 2^c when
+        // the top window is full (253 = 11 * 23: every vector of 2^14 .. 2^15 - 1 pairs, scalars >= 2^252); its window
+        // gets 2^c buckets so that buckets[d - 1] stays in range
+        const size_t nbuckets = (size_t)1 << (w + 1 == digits_count ? c : c - 1);
+        std::vector<Jac<F>> buckets(nbuckets, Jac<F>::identity());
         for (size_t i = 0; i < n; i++) {
             const int64_t d = digits[i * digits_count + w];
             if (d > 0) buckets[d - 1] = jmadd(buckets[d - 1], pts[i]);

@@ -174,3 +174,24 @@ def test_c1_host_pieces_key_generation_and_proofs_of_knowledge():
     # the same seed gives the same key; a different transcript digest gives different G2 points
     pk2, k2 = H.key_generation(cv, H.derive_rng_from_seed(b"seed-0"), digest)
     assert H.public_key_bytes(cv, pk2) == blob and k2 == (tau, alpha, beta)
+
+
+def test_oracle_bucket_msm_small_and_full_top_window():
+    """oracle.cpp msm_pippenger (the reference arm's msm_bigint restatement) against the naive sum, and at a size whose
+    window width divides the scalar length (2^14 <= n < 2^15 -> c = 11, 253 = 11 * 23): the last signed digit then
+    reaches 2^c for scalars >= 2^252 — a bench run that landed on a 2^15-power sample corrupted the heap there."""
+    cv, g = R.BLS12_377, R.BLS12_377.g1
+    rng = random.Random(2024)
+    for n in (1, 31, 200):
+        pts = [g.mul(g.gen, rng.randrange(1, cv.r)) for _ in range(n)]
+        ks = [rng.randrange(cv.r) for _ in range(n)]
+        blob = b"".join(g.encode(p, False) for p in pts)
+        assert O.msm_pippenger(0, 0, blob, False, n, ks) == O.msm(0, 0, blob, False, n, ks), n
+    n = 20000
+    mult = [rng.randrange(1, cv.r) for _ in range(8)]
+    enc = [g.encode(g.mul(g.gen, a), False) for a in mult]
+    ks = [rng.randrange(1 << 252, cv.r) if i % 3 else rng.randrange(cv.r) for i in range(n)]
+    ks[0], ks[1] = cv.r - 1, 1 << 252
+    blob = b"".join(enc[i % 8] for i in range(n))
+    want = g.encode(g.mul(g.gen, sum(k * mult[i % 8] for i, k in enumerate(ks)) % cv.r), False)
+    assert O.msm_pippenger(0, 0, blob, False, n, ks) == want

@@ -1,4 +1,4 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_pairing.py -q -x > gpurun_out/r02_gpu_tests_pairing_units.log 2>&1; tail -3 gpurun_out/r02_gpu_tests_pairing_units.log
-python tools/extra_bench.py pairing > gpurun_out/pairing_latency_units.jsonl; cat gpurun_out/pairing_latency_units.jsonl
+python -X faulthandler bench.py > gpurun_out/dbg_bench.json 2> gpurun_out/dbg_bench.err; echo "exit $?"
+tail -60 gpurun_out/dbg_bench.err; tail -c 300 gpurun_out/dbg_bench.json
