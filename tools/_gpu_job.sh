@@ -1,4 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python -X faulthandler bench.py > gpurun_out/dbg_bench.json 2> gpurun_out/dbg_bench.err; echo "exit $?"
-tail -60 gpurun_out/dbg_bench.err; tail -c 300 gpurun_out/dbg_bench.json
+N=${NGPU:-8}
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02_bench_final_n$N.json 2> gpurun_out/bench_n$N.err ) 2>&1 | tail -3
+tail -c 300 gpurun_out/r02_bench_final_n$N.json; grep "bench " gpurun_out/bench_n$N.err | tail -5
