@@ -108,7 +108,12 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     }
     const int W = (nbits + c - 1) / c;
     const uint32_t B = 1u << c;
-    const uint32_t seglen = B >= 1024 ? 32 : (B >= 256 ? B / 256 : 1), nseg = B / seglen;
+    // bucket segments of the running-sum reduction: one thread per (sum, window, segment), and the kernel is pure
+    // latency (2 * seglen + ~20 additions in sequence per thread), so segments shrink while all the threads still fit
+    // the machine at once (2 blocks of 128 threads per SM at ~250 registers)
+    uint32_t seglen = B >= 1024 ? 32 : (B >= 256 ? B / 256 : 1);
+    while (seglen > 8 && (uint64_t)2 * W * (B / (seglen / 2)) <= 148u * 2 * 128) seglen /= 2;
+    const uint32_t nseg = B / seglen;
     const size_t fw = o.coord_words;
 
     // slab layout

@@ -39,3 +39,29 @@ python tools/pageable_probe.py 22 >> gpurun_out/host_buffer_probe.jsonl
 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests.log 2>&1
 SS_TEST_FULL=1 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests_full_sizes.log 2>&1
 # A/B variants (profiles/r01_ab_variants.md): tools/build_variant.sh <name> "<-D flags>" then tools/ab_bench.sh
+
+# ---- round 2 -----------------------------------------------------------------------------------------------------
+# r02_bench_default_final.json, r02_bench_reference_arm_final.json, r02_bench_final_n{2,4,8}.json
+python bench.py > gpurun_out/r02_bench_default_final.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm_final.json
+for n in 2 4 8; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/r02_bench_final_n$n.json || true
+done
+# r02_ncu_launches_power18_final.csv (one ncu pass per box call; the same command ran plain first)
+CMD="python bench.py --power 18 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
+SS_CONCURRENT_VECTORS=0 $CMD > /dev/null
+SS_CONCURRENT_VECTORS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
+  --log-file gpurun_out/r02_ncu_launches_power18_final.csv $CMD > /dev/null
+# r02_ncu_full_final.json (--set full of the hot kernels, condensed by tools/ncu_summary.py)
+SS_CONCURRENT_VECTORS=0 ncu --set full --clock-control none \
+  -k regex:"k_scalar_mul|k_subgroup|k_msm_accumulate|k_msm_reduce|k_decode|k_normalize|k_same_ratio" -s 40 -c 24 -o /tmp/ncu_final -f $CMD > /dev/null
+ncu -i /tmp/ncu_final.ncu-rep --page raw --csv > /tmp/ncu_final_raw.csv
+python tools/ncu_summary.py /tmp/ncu_final_raw.csv gpurun_out/r02_ncu_full_final.json "<command>"
+# r02_pairing_latency.jsonl, r02_extra_bench_bw6_phase2.jsonl
+python tools/extra_bench.py pairing > gpurun_out/pairing_latency.jsonl
+python tools/extra_bench.py 16 20 > gpurun_out/extra.jsonl
+# strong-scaling tail: one GPU playing rank 1 of 8
+python tools/shard_probe.py 22 8 1
+# r02_sass_summary.md
+python tools/sass_summary.py > profiles/r02_sass_summary.md
