@@ -180,6 +180,38 @@ def cpu_baseline(budget_s=20.0):
             "contribute_powers_per_s": (1 << k) / tc, "verify_powers_per_s": (1 << k) / tv}
 
 
+NCU_FULL = os.path.join("profiles", "r02_ncu_full_final.json")
+
+
+def ncu_traffic(name, d):
+    """`traffic` of the dominant kernel from the committed same-round `ncu --set full` capture (dram__bytes_read.sum +
+    dram__bytes_write.sum of its largest launch there), scaled by elements to this run's average launch — or null."""
+    none = {"traffic": None, "traffic_note": "no ncu --set full capture of this kernel under %s" % NCU_FULL}
+    try:
+        cap = json.load(open(os.path.join(ROOT, NCU_FULL)))
+        tag = "k_scalar_mul<Bls377G2>" if ".g2" in name else "k_scalar_mul<Bls377G1>"
+        best = None
+        for rec in cap["launches"]:
+            if tag in rec["Kernel Name"]:
+                grid = int(rec["Grid Size"].strip("()").split(",")[0])
+                block = int(rec["Block Size"].strip("()").split(",")[0])
+                if best is None or grid > best[0]:
+                    to_b = lambda t: float(t.split()[0]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[t.split()[1]]  # noqa: E731
+                    best = (grid, grid * block, to_b(rec["dram__bytes_read.sum"]) + to_b(rec["dram__bytes_write.sum"]))
+        if not best or best[1] < 1024:
+            return none
+        per_launch = d["elements"] / max(1, d["launches"])
+        return {"traffic": best[2] / best[1] * per_launch, "traffic_unit": "bytes per launch",
+                "traffic_source": "%s: %.0f MB DRAM read+write for a %d-thread launch of this kernel (ncu --set full, same build), "
+                                  "scaled by elements to this run's %.0f-element launches; algorithmic bytes are %d per element — "
+                                  "the excess is the per-thread window table and Jacobian spills in local memory of an "
+                                  "integer-pipe-bound kernel" % (NCU_FULL, best[2] / 1e6, best[1], per_launch,
+                                                                  (192 + 96) if ".g2" in name else (96 + 48))}
+    except Exception as exc:
+        none["traffic_note"] += " (%r)" % (exc,)
+        return none
+
+
 def run_extras(S, R, O, bw6_power, phase2_log2):
     """One-step measurements of the other BASELINE configs through the host-buffer C ABI, reported beside the headline
     (`extras`), never part of `value`:  C3 = BW6-761 phase-1 verify (subgroup checks + power_pairs MSM + the four device
@@ -550,9 +582,7 @@ def main():
                     "tests/test_device_algos_emul.py) of the dominant kernel / its measured duration / measured peak",
             "achieved": ex["achieved"], "frac": ex["frac"], "mac32_per_element": ex["mac32_per_element"],
             "avg_launch_ms": ex["avg_launch_ms"], "kernel_share_of_contribute_step": d["ms"] / total_ms,
-            "traffic": None,
-            "traffic_note": "no same-round ncu --set full capture is read at run time; measured DRAM bytes per launch are in "
-                            "profiles/ (see profiles/README.md)",
+            **ncu_traffic(name, d),
             "second_kernel": next((executed(n2, d2) for n2, d2 in smul.items() if n2 != name), None),
             "vs_reference_algorithm": {
                 "what": "W_ref (reference double-and-add, SURVEY §8d) x elements / duration / peak — a speed-up-vs-reference-"
