@@ -368,6 +368,11 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
     }
     const size_t status_bytes = align_up(ntiles * 8, 256);
     int rc = SS_OK;
+    bool have_pending = false;
+    uint8_t* pend_dst = nullptr;
+    const uint8_t* pend_src = nullptr;
+    size_t pend_bytes = 0;
+    cudaStream_t pend_stream = nullptr;
     for (size_t t = 0; t < ntiles; t++) {
         const uint64_t e0 = t * T, cnt = std::min<uint64_t>(T, j.n - e0);
         Lane* ln = lg[t % nl].l;
@@ -428,8 +433,20 @@ int run_vector_on(int device, const VectorJob& j, bool host, cudaStream_t user_s
         na.out_compressed = j.out_c;
         na.threads = normalize_threads(cnt);
         { ProfScope ps("k_normalize_encode", o.name, cnt, s); o.normalize_encode(na, s); }
-        if (host) CU(cudaMemcpyAsync(j.out + e0 * osz, d_out, cnt * osz, cudaMemcpyDeviceToHost, s));
+        // Output copies run ONE TILE BEHIND: a device-to-host copy into PAGEABLE memory (the callers' mmaps) blocks the
+        // issuing thread until the tile's kernels have finished, so issuing it right here would keep tile t + 1 (other
+        // lane) from being enqueued until tile t is completely done.  Its slab region is safe: the lane is reused by
+        // tile t + 2, enqueued after the copy on the same stream.  For pinned buffers the order is immaterial.
+        if (host) {
+            if (have_pending) CU(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, pend_stream));
+            pend_dst = j.out + e0 * osz;
+            pend_src = d_out;
+            pend_bytes = cnt * osz;
+            pend_stream = s;
+            have_pending = true;
+        }
     }
+    if (have_pending) CU(cudaMemcpyAsync(pend_dst, pend_src, pend_bytes, cudaMemcpyDeviceToHost, pend_stream));
     CU(cudaGetLastError());
     for (int k = 0; k < nl; k++) CU(cudaStreamSynchronize((!host && user_stream) ? user_stream : lg[k].l->stream));
     if (ev_init) cudaEventDestroy(ev_init);
