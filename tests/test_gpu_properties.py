@@ -2,7 +2,8 @@
 (BASELINE.json configs): contribute is a group action, so contributing (tau, alpha, beta) and then their
 inverses must give back the original accumulator byte for byte; a verified response must satisfy
 sx = tau * s for every vector; decompress(compress(x)) = x; phase-2 batch_mul by delta then delta^-1 is the
-identity.  Sizes: 2^18 powers by default, SS_TEST_FULL=1 runs the 2^20 / BW6 2^16 sizes of the configs."""
+identity.  Sizes: 2^18 powers by default; SS_TEST_FULL=1 runs BASELINE.json's own sizes — 2^22 BLS12-377 (configs[3], the
+metric's configuration) and 2^21 BW6-761 (configs[2]); logs under profiles/."""
 import hashlib
 import os
 import random
@@ -30,7 +31,7 @@ def _blank(cv, rp):
     return bytes(out)
 
 
-@pytest.mark.parametrize("curve,power", [("bls12_377", 20 if FULL else 18), ("bw6_761", 16 if FULL else 12)])
+@pytest.mark.parametrize("curve,power", [("bls12_377", 22 if FULL else 18), ("bw6_761", 21 if FULL else 12)])
 def test_contribute_inverse_roundtrip_and_verify(curve, power):
     cv = R.CURVES[curve]
     cid = S.BLS12_377 if curve == "bls12_377" else S.BW6_761
