@@ -1,3 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tee gpurun_out/r02_gpu_multi_tests_2gpu_final.log | tail -3
+N=${NGPU:-8}
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02_bench_final_n$N.json 2> gpurun_out/bench_n$N.err ) 2>&1 | tail -3
+tail -c 200 gpurun_out/r02_bench_final_n$N.json; grep "bench " gpurun_out/bench_n$N.err | tail -5
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/ref_n$N.json 2>/dev/null ) 2>&1 | tail -3; head -c 300 gpurun_out/ref_n$N.json
