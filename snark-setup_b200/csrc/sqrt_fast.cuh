@@ -3,7 +3,7 @@
 //
 // BLS12-377 Fq has 2-adicity 46, the worst case for Tonelli-Shanks: the textbook loop costs ~1000
 // data-dependent squarings per element and every lane of a warp waits for the slowest one.  Here
-//   x = a^((t+1)/2), b = a^t = zeta^e                       one fixed-exponent power, 4-bit windows
+//   x = a^((t+1)/2), b = a^t = zeta^e                       one fixed-exponent power, 5-bit sliding windows
 //   e recovered by Pohlig-Hellman in chunks [6,8,8,8,8,8]   40 squarings + 15 table multiplications,
 //                                                           chunk lookups through a 1024-slot hash
 //   sqrt(a) = x * zeta^(-e/2)                               6 table multiplications
@@ -21,34 +21,6 @@
 #include "sqrt_tables_gen.cuh"
 
 namespace ss {
-
-// a^e for an exponent shared by all threads (limb accessor), 4-bit fixed windows
-template <class P, class E>
-SS_HD Fp<P> fp_pow_w4(const Fp<P>& a, E exp_limb, int nlimbs) {
-    Fp<P> tab[16];
-    tab[0] = Fp<P>::one();
-    tab[1] = a;
-#pragma unroll 1
-    for (int i = 2; i < 16; i++) tab[i] = fp_mul(tab[i - 1], a);
-    Fp<P> r = Fp<P>::one();
-    bool started = false;
-    for (int i = nlimbs - 1; i >= 0; i--) {
-        const uint32_t w = exp_limb(i);
-#pragma unroll 1
-        for (int s = 28; s >= 0; s -= 4) {
-            const uint32_t d = (w >> s) & 15u;
-            if (started) {
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) r = fp_sqr(r);
-            }
-            if (d) {
-                r = started ? fp_mul(r, tab[d]) : tab[d];
-                started = true;
-            }
-        }
-    }
-    return r;
-}
 
 using FqB = Fp<Bls377Fq>;
 
@@ -118,7 +90,7 @@ SS_HD FqB sqrt_zeta_neg_half(uint64_t E) {
 
 // w = a^((t-1)/2), x = a w, e = dlog(a^t).  a != 0.
 SS_HD bool sqrt_parts(const FqB& a, FqB& w, FqB& x, uint64_t& e) {
-    w = fp_pow_w4<Bls377Fq>(a, [](int i) { return Bls377Fq::tm1h(i); }, 12);
+    w = fp_pow_win<5>(a, [](int i) { return Bls377Fq::tm1h(i); }, 12);  // 5-bit sliding windows: 331 squarings + 71 multiplications
     x = fp_mul(a, w);
     FqB b = fp_mul(x, w);
     return sqrt_dlog46(b, e);
@@ -187,7 +159,7 @@ SS_HD bool fp_sqrt_any(const Fp<P>& a, Fp<P>& out) {
         return true;
     }
     if (P::P3MOD4) {
-        Fp<P> r = fp_pow_w4<P>(a, [](int i) { return P::pp1q(i); }, P::N);
+        Fp<P> r = fp_pow_win<5>(a, [](int i) { return P::pp1q(i); }, P::N);
         out = r;
         return fp_sqr(r) == a;
     }
