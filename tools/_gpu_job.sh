@@ -1,11 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python bench.py --power 20 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-extras > gpurun_out/ab_sw.json 2>/dev/null
-python - <<P
-import json
-for l in open('gpurun_out/ab_sw.json'):
-    if l.startswith('{'):
-        d=json.loads(l); r=d['roofline']; print('sw', d['value'], d['legs']['contribute']['ms_per_step'], d['legs']['verify']['ms_per_step']); print(r['kernels_ms_contribute']); print(r['kernels_ms_verify'])
-P
-python tools/extra_bench.py pairing
+N=${NGPU:-8}
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02_bench_final_n$N.json 2> gpurun_out/bench_n$N.err ) 2>&1 | tail -3
+tail -c 200 gpurun_out/r02_bench_final_n$N.json; grep "bench " gpurun_out/bench_n$N.err | tail -5
