@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-N=${NGPU:-8}
-( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02_bench_final_n$N.json 2> gpurun_out/bench_n$N.err ) 2>&1 | tail -3
-tail -c 200 gpurun_out/r02_bench_final_n$N.json; grep "bench " gpurun_out/bench_n$N.err | tail -5
+export SS_CONCURRENT_VECTORS=0
+python bench.py --power 18 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/plain_power18_final.json 2>/dev/null; echo "plain exit $?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r02_ncu_launches_power18_final.csv python bench.py --power 18 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > /dev/null 2> gpurun_out/ncu.err; echo "ncu exit $?"
