@@ -45,3 +45,51 @@ def test_b200_arm_needs_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=600, cwd=ROOT)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_roofline_traffic_comes_from_the_named_capture():
+    """`roofline.traffic` is read from the committed same-round ncu --set full summary and names it; a kernel without
+    a capture gives null, never a made-up figure."""
+    b = _load_bench()
+    t = b.ncu_traffic("k_scalar_mul<bls12_377.g1>", {"elements": 1 << 24, "launches": 16, "ms": 1000.0})
+    cap = json.load(open(os.path.join(ROOT, b.NCU_FULL)))
+    rec = max((r for r in cap["launches"] if "k_scalar_mul<Bls377G1>" in r["Kernel Name"]),
+              key=lambda r: int(r["Grid Size"].strip("()").split(",")[0]))
+    threads = int(rec["Grid Size"].strip("()").split(",")[0]) * int(rec["Block Size"].strip("()").split(",")[0])
+    mb = float(rec["dram__bytes_read.sum"].split()[0]) + float(rec["dram__bytes_write.sum"].split()[0])
+    assert rec["dram__bytes_read.sum"].split()[1] == "Mbyte" and rec["dram__bytes_write.sum"].split()[1] == "Mbyte"
+    assert abs(t["traffic"] - mb * 1e6 / threads * (1 << 20)) < 1e-3 * t["traffic"]
+    assert b.NCU_FULL in t["traffic_source"]
+    # only a one-thread G2 launch (beta_g2) is in the capture: null, with the reason
+    none = b.ncu_traffic("k_scalar_mul<bls12_377.g2>", {"elements": 1 << 20, "launches": 2, "ms": 100.0})
+    assert none["traffic"] is None and "traffic_note" in none
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The evidence files of the final build are what bench.py printed: one JSON line with every key of the contract."""
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    for name, n in (("r02_bench_default_final.json", 1), ("r02_bench_final_n2.json", 2), ("r02_bench_final_n4.json", 4),
+                    ("r02_bench_final_n8.json", 8)):
+        lines = [l for l in open(os.path.join(ROOT, "profiles", name)) if l.startswith("{")]
+        assert len(lines) == 1, name
+        d = json.loads(lines[0])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in d, (name, key)
+        assert d["metric"] == base["metric"] and d["n_gpus"] == n and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert "2^22" in d["config"]["workload"] and d["scaling"] == "strong" and d["vs_baseline"] is None
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"] * 1.01
+        assert abs(d["value"] - (1 << 22) / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+        r = d["roofline"]
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+        assert not d["clocks"]["reasons"] and d["verdict_all_steps"] is True and d["parity_spot_check"] is True
+        if n == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
