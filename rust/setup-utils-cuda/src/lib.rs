@@ -5,7 +5,9 @@
 //! check_same_ratio}` (setup-utils/src/helpers.rs:32,56,75,371,388,406,410; elements.rs:123),
 //! `phase1::helpers::buffers::apply_powers` (phase1/src/helpers/buffers.rs:77), `Phase1::computation`
 //! (phase1/src/computation.rs:16-25) and the per-vector half of `Phase1::verification`
-//! (phase1/src/verification.rs:26-40,217-411) become one call each.
+//! (phase1/src/verification.rs:26-40,217-411) become one call each; further down the SURVEY §8f rows: verdicts from
+//! ratio pairs, accumulator re-layout (`Phase1::aggregation` / `split` / `decompress`), `Groth16Params::new`, group
+//! IFFT / H query and the QAP row sums of phase 2.
 //!
 //! The seam is at byte-slice granularity: arkworks' `Affine<P>` is not `repr(C)`, so the generic in-memory entry
 //! points serialise to the canonical uncompressed form, call the engine, and read the result back; the phase1
@@ -151,6 +153,12 @@ fn points_from<C: AffineRepr>(bytes: &[u8], out: &mut [C]) -> Result<()> {
         *o = C::deserialize_with_mode(&bytes[i * sz..(i + 1) * sz], Compress::No, Validate::No)?;
     }
     Ok(())
+}
+
+fn read_points<C: AffineRepr>(bytes: &[u8], n: usize) -> Vec<C> {
+    let mut out = vec![C::zero(); n];
+    points_from(bytes, &mut out).expect("engine returns canonical points");
+    out
 }
 
 fn params_of<E: CudaCurve>(p: &Phase1Parameters<E>) -> ffi::SsPhase1Params {
@@ -630,4 +638,140 @@ pub fn groth16_params_new<E: CudaCurve>(
         )
     })?;
     Ok(out)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// verdicts from pairs, accumulator re-layout, group transforms, QAP rows
+// ------------------------------------------------------------------------------------------------------------------
+
+/// `check_power_ratios` / `check_power_ratios_g2` (phase1/src/helpers/accumulator.rs:56-91) of the four vectors from
+/// their (s, sx) pairs blob — the whole-response blob or the `ss_phase1_reduce_partial_pairs` of the shards' blobs —
+/// against `g1_check = (tau_g1[0], tau_g1[1])` and `g2_check = (tau_g2[0], tau_g2[1])` (verification.rs:58-71), the four
+/// pairing checks run on the device.  `Err(VerificationError::InvalidRatio)` names the failing vector.
+pub fn check_ratio_pairs<E: CudaCurve>(
+    pairs_blob: &[u8],
+    g1_check: &(E::G1Affine, E::G1Affine),
+    g2_check: &(E::G2Affine, E::G2Affine),
+) -> Result<()> {
+    assert_eq!(pairs_blob.len(), unsafe { ffi::ss_phase1_pairs_size(E::CURVE_ID) });
+    let a = points_bytes(&[g1_check.0, g1_check.1]);
+    let b = points_bytes(&[g2_check.0, g2_check.1]);
+    check(unsafe { ffi::ss_phase1_check_ratio_pairs(E::CURVE_ID, pairs_blob.as_ptr(), a.as_ptr(), b.as_ptr()) })
+}
+
+/// Several `check_same_ratio` (setup-utils/src/helpers.rs:406-424) in one launch; `Err` carries the first failing index
+/// in `ss_last_error().index`.
+pub fn check_same_ratio_batch<E: CudaCurve>(
+    g1: &[(E::G1Affine, E::G1Affine)],
+    g2: &[(E::G2Affine, E::G2Affine)],
+) -> core::result::Result<(), usize> {
+    assert_eq!(g1.len(), g2.len());
+    let a: Vec<E::G1Affine> = g1.iter().flat_map(|p| [p.0, p.1]).collect();
+    let b: Vec<E::G2Affine> = g2.iter().flat_map(|p| [p.0, p.1]).collect();
+    let (ab, bb) = (points_bytes(&a), points_bytes(&b));
+    let mut first_bad: c_int = -1;
+    let rc = unsafe { ffi::ss_check_same_ratio_batch(E::CURVE_ID, ab.as_ptr(), bb.as_ptr(), g1.len() as c_int, &mut first_bad) };
+    match rc {
+        0 => Ok(()),
+        10 => Err(first_bad as usize),
+        _ => {
+            check(rc).expect("pairing inputs are canonical points");
+            Ok(())
+        }
+    }
+}
+
+/// One iteration of `Phase1::aggregation` (phase1/src/aggregation.rs:11-180): the vectors of the chunk
+/// `chunk_parameters.chunk_index` are written into the full accumulator (beta_g2 comes from chunk 0).
+pub fn phase1_aggregate_chunk<E: CudaCurve>(
+    chunk: &[u8],
+    compressed_chunk: UseCompression,
+    full: &mut [u8],
+    compressed_full: UseCompression,
+    chunk_parameters: &Phase1Parameters<E>,
+) -> Result<()> {
+    let p = params_of(chunk_parameters);
+    check(unsafe {
+        ffi::ss_phase1_aggregate_chunk(&p, chunk.as_ptr(), chunk.len(), flag(compressed_chunk), full.as_mut_ptr(), full.len(), flag(compressed_full))
+    })
+}
+
+/// One iteration of `Phase1::split` (phase1/src/aggregation.rs:189-353): the reverse of `phase1_aggregate_chunk`.
+pub fn phase1_split_chunk<E: CudaCurve>(
+    full: &[u8],
+    compressed_full: UseCompression,
+    chunk: &mut [u8],
+    compressed_chunk: UseCompression,
+    chunk_parameters: &Phase1Parameters<E>,
+) -> Result<()> {
+    let p = params_of(chunk_parameters);
+    check(unsafe {
+        ffi::ss_phase1_split_chunk(&p, full.as_ptr(), full.len(), flag(compressed_full), chunk.as_mut_ptr(), chunk.len(), flag(compressed_chunk))
+    })
+}
+
+/// `helpers::accumulator::decompress` (phase1/src/helpers/accumulator.rs:200-301): compressed accumulator ->
+/// uncompressed, elements read with `check_input_for_correctness`.
+pub fn phase1_decompress<E: CudaCurve>(
+    input: &[u8],
+    output: &mut [u8],
+    check_input_for_correctness: CheckForCorrectness,
+    parameters: &Phase1Parameters<E>,
+) -> Result<()> {
+    let p = params_of(parameters);
+    check(unsafe {
+        ffi::ss_phase1_decompress(&p, input.as_ptr(), input.len(), check_mode(check_input_for_correctness), output.as_mut_ptr(), output.len())
+    })
+}
+
+/// `to_coeffs` = `domain.ifft` over curve points (setup-utils/src/groth16_utils.rs:44-53); `n` a power of two.
+pub fn group_ifft<C: CudaGroup>(points: &[C]) -> Result<Vec<C>> {
+    let input = points_bytes(points);
+    let mut out = vec![0u8; input.len()];
+    check(unsafe {
+        ffi::ss_group_ifft(C::CURVE_ID, C::GROUP_ID, input.as_ptr(), 0, check_mode(CheckForCorrectness::No), points.len(), out.as_mut_ptr(), 0)
+    })?;
+    Ok(read_points::<C>(&out, points.len()))
+}
+
+/// `h_query_groth16` (setup-utils/src/groth16_utils.rs:59-63): out_i = powers[i + degree] - powers[i], i < degree - 1.
+pub fn h_query_groth16<C: CudaGroup>(powers: &[C], degree: usize) -> Result<Vec<C>> {
+    let input = points_bytes(powers);
+    let n_out = degree.saturating_sub(1);
+    let mut out = vec![0u8; n_out * C::zero().uncompressed_size()];
+    check(unsafe {
+        ffi::ss_h_query_groth16(C::CURVE_ID, input.as_ptr(), 0, check_mode(CheckForCorrectness::No), powers.len(), degree, out.as_mut_ptr(), 0)
+    })?;
+    Ok(read_points::<C>(&out, n_out))
+}
+
+/// `dot_product_vec` + `normalize_batch` (phase2/src/polynomial.rs:30-47,75-94): one point per CSR row,
+/// out_v = sum over the row's entries of coeffs[e] * bases[index[e]].
+pub fn qap_dot_product<C: CudaGroup>(
+    bases: &[C],
+    row_ptr: &[u64],
+    index: &[u32],
+    coeffs: &[C::ScalarField],
+) -> Result<Vec<C>> {
+    assert!(!row_ptr.is_empty() && index.len() == coeffs.len() && *row_ptr.last().unwrap() as usize == index.len());
+    let rows = row_ptr.len() - 1;
+    let (bb, cb) = (points_bytes(bases), scalars_bytes(coeffs));
+    let mut out = vec![0u8; rows * C::zero().uncompressed_size()];
+    check(unsafe {
+        ffi::ss_qap_dot_product(
+            C::CURVE_ID,
+            C::GROUP_ID,
+            bb.as_ptr(),
+            0,
+            check_mode(CheckForCorrectness::No),
+            bases.len(),
+            row_ptr.as_ptr(),
+            index.as_ptr(),
+            cb.as_ptr(),
+            rows,
+            out.as_mut_ptr(),
+            0,
+        )
+    })?;
+    Ok(read_points::<C>(&out, rows))
 }

@@ -128,3 +128,41 @@ fn cuda_helpers_match_setup_utils() {
     assert!(!same_ratio::<Bls12_377>(&setup_utils_cuda::power_pairs(&v), &(G2Affine::generator(), gx)));
     assert!(setup_utils_cuda::check_subgroup(&bases1, SubgroupCheckMode::Auto).is_ok());
 }
+
+/// The sharded verification loop: three index-range shards of one response, partial pairs added, verdict from the pairs
+/// — and the re-layout wrappers against the reference's `decompress`.
+#[test]
+fn cuda_sharded_verification_and_relayout() {
+    let params = Phase1Parameters::<Bls12_377>::new_full(ProvingSystem::Groth16, 8, 64);
+    let (input, _) = generate_input(&params, UseCompression::No);
+    let mut rng = derive_rng_from_seed(b"parity-4");
+    let (_, privkey) = Phase1::key_generation(&mut rng, &[0u8; 64]).unwrap();
+    let mut response = generate_output(&params, UseCompression::Yes);
+    Phase1::computation(&input, &mut response, UseCompression::No, UseCompression::Yes, CheckForCorrectness::No, BatchExpMode::Auto, &privkey, &params)
+        .unwrap();
+    let n_resp = response.len() - params.public_key_size;
+    let mut new_challenge = vec![0u8; params.accumulator_size];
+    let blobs: Vec<Vec<u8>> = (0..3u32)
+        .map(|s| {
+            setup_utils_cuda::phase1_verification_vectors_shard(
+                &response[..n_resp], Some(&mut new_challenge[..]), UseCompression::Yes, UseCompression::No, SubgroupCheckMode::Auto, true, &params, (s, 3),
+            )
+            .unwrap()
+        })
+        .collect();
+    let pairs = setup_utils_cuda::reduce_partial_pairs::<Bls12_377>(&blobs).unwrap();
+    let acc = Phase1::deserialize(&response[..n_resp], UseCompression::Yes, CheckForCorrectness::Full, &params).unwrap();
+    let g1 = (acc.tau_powers_g1[0], acc.tau_powers_g1[1]);
+    let g2 = (acc.tau_powers_g2[0], acc.tau_powers_g2[1]);
+    assert!(same_ratio::<Bls12_377>(&pairs.tau_g1, &g2));
+    assert!(same_ratio::<Bls12_377>(&g1, &pairs.tau_g2));
+    assert!(same_ratio::<Bls12_377>(&pairs.alpha_g1, &g2));
+    assert!(same_ratio::<Bls12_377>(&pairs.beta_g1, &g2));
+    // the new challenge the shards wrote is the reference's decompressed response
+    let mut want = vec![0u8; params.accumulator_size];
+    phase1::helpers::accumulator::decompress(&response[..n_resp], &mut want, CheckForCorrectness::No, &params).unwrap();
+    assert_eq!(want[64..], new_challenge[64..]);
+    let mut got = vec![0u8; params.accumulator_size];
+    setup_utils_cuda::phase1_decompress(&response[..n_resp], &mut got, CheckForCorrectness::No, &params).unwrap();
+    assert_eq!(want[64..], got[64..]);
+}
