@@ -205,7 +205,7 @@ bool concurrent_vectors() {
 }
 
 // Elements per device tile.  k_scalar_mul does the same work in every thread, so its blocks finish in waves:
-// the default is 8 whole waves of the G1 kernel (148 SMs x 4 resident blocks x 128 threads = 75 776
+// the default is 16 whole waves of the G1 kernel (148 SMs x 4 resident blocks x 128 threads = 75 776
 // elements per wave; the G2 kernel's waves are half that).  Measured (profiles/r01_ab_variants.md): wave quantisation is
 // NOT visible (2^18: 251 ms, 4 waves: 248 ms), larger tiles win through fewer normalisation tails: 8 waves +1.3 % over 2^18
 // (round 1), 16 waves another +0.85 % on the 2^22 contribute (1657.7 -> 1643.7 ms, profiles/r02_ab_variants.md).

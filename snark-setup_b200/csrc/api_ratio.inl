@@ -89,7 +89,8 @@ int run_ratio_vector(int device, const RatioJob& j, bool host, cudaStream_t user
     if (j.do_ratio && pairs == 0) return fail(SS_ERR_BATCH_TOO_SMALL, 0, 0, 0, "%s: ratio check needs at least 2 elements", j.what);
     const size_t isz = j.compressed ? o.csize : o.usize, osz = j.out_compressed ? o.csize : o.usize;
     // ratio jobs use larger tiles than batch_exp: W*B bucket threads per tile must be several waves of the
-    // machine (2^20 pairs -> c = 15 -> 9 x 32768 buckets), see profiles/r01_ncu_msm_accumulate.md
+    // machine (2^21 pairs -> c = 16 -> 8 x 65536 buckets, 16 points per bucket on average), see
+    // profiles/r02_ab_variants.md
     const uint64_t own_total = j.own ? j.own : j.n;
     const size_t T = std::min<uint64_t>(j.do_ratio ? ratio_tile_elems() : tile_elems(), own_total);
     const size_t ntiles = (own_total + T - 1) / T;
