@@ -148,7 +148,7 @@ static __global__ void k_msm_scatter(MsmSortArgs a) {
 // with 16-byte vector accesses.  (The limb-major SoA form used elsewhere puts the 3*FW words of one
 // bucket 2*W*B*4 bytes apart; with buckets visited in sorted-by-run-length order that is 36 scattered
 // sectors per bucket and, for some power-of-two strides, pathological: 3.2 s instead of 9 ms for a
-// 2^19-element vector, profiles/r01_msm_layout.md.)  `stride` is kept in the signature for symmetry.
+// 2^19-element vector, profiles/r01_ab_variants.md.)  `stride` is kept in the signature for symmetry.
 template <class G>
 SS_D Jac<typename G::F> load_jac(const uint32_t* base, uint64_t /*stride*/, uint64_t i) {
     using FW = FieldWords<typename G::F>;
