@@ -58,6 +58,13 @@ SS_CONCURRENT_VECTORS=0 ncu --set full --clock-control none \
   -k regex:"k_scalar_mul|k_subgroup|k_msm_accumulate|k_msm_reduce|k_decode|k_normalize|k_same_ratio" -s 40 -c 24 -o /tmp/ncu_final -f $CMD > /dev/null
 ncu -i /tmp/ncu_final.ncu-rep --page raw --csv > /tmp/ncu_final_raw.csv
 python tools/ncu_summary.py /tmp/ncu_final_raw.csv gpurun_out/r02_ncu_full_final.json "<command>"
+# r02_ncu_full_scalar_mul_g2.json (the full-size G2 launch needs the demangled name to be selected)
+SS_CONCURRENT_VECTORS=0 ncu --set full --clock-control none --kernel-name-base demangled \
+  -k regex:"k_scalar_mul<ss::Bls377G2>" -c 2 -o /tmp/ncu_g2 -f $CMD > /dev/null
+ncu -i /tmp/ncu_g2.ncu-rep --page raw --csv > /tmp/ncu_g2_raw.csv
+python tools/ncu_summary.py /tmp/ncu_g2_raw.csv gpurun_out/r02_ncu_full_scalar_mul_g2.json "<command>"
+# r02_gpu_tests_full_sizes.log
+SS_TEST_FULL=1 python -m pytest tests/test_gpu_properties.py -m gpu -q > gpurun_out/r02_gpu_tests_full_sizes.log 2>&1
 # r02_pairing_latency.jsonl, r02_extra_bench_bw6_phase2.jsonl
 python tools/extra_bench.py pairing > gpurun_out/pairing_latency.jsonl
 python tools/extra_bench.py 16 20 > gpurun_out/extra.jsonl
